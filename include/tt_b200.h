@@ -1,0 +1,160 @@
+/*
+ * tt_b200.h — C-ABI of the B200-native serving hot path of the two-tower recommender.
+ *
+ * This is the drop-in boundary: every entry point takes plain device pointers, sizes and a
+ * CUDA stream (passed as void* so that no CUDA header is needed by the binder).  No torch
+ * types, no ownership transfer: the caller allocates every output and the workspace.
+ * All functions return 0 on success and a non-zero TT_ERR_* code otherwise;
+ * tt_last_error() returns a thread-local, human-readable message for the last failure.
+ *
+ * The reference (HeikalPro/two-tower-model-v2) has no FFI for this path; its boundary is
+ * the Python class API of two modules.  Each entry point cites the reference lines whose
+ * arithmetic it replaces:
+ *
+ *   src/models/buyer_tower.py:43-68    weighted_average        -> tt_pool_weighted[_gather]
+ *   src/models/buyer_tower.py:70-101   attention_aggregation   -> tt_attention_logits + tt_pool_attention[_gather]
+ *   src/inference/vector_db.py:44-54   build_index (normalise + IndexFlatIP.add) -> tt_flat_build
+ *   src/inference/vector_db.py:152-160 retrieve  (renormalise + IndexFlatIP.search) -> tt_flat_search
+ *   src/inference/vector_db.py:189-197 retrieve_batch (same, nq > 1)            -> tt_flat_search
+ *   (absent in the reference)          cross-GPU merge of per-shard top-K       -> tt_topk_merge
+ *
+ * There is no CPU implementation behind any of these symbols: without a CUDA device they
+ * return TT_ERR_CUDA.
+ */
+#ifndef TT_B200_H_
+#define TT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_B200_ABI_VERSION 1
+
+enum {
+  TT_OK = 0,
+  TT_ERR_INVALID = 1,   /* bad argument (null pointer, size, alignment, unsupported shape) */
+  TT_ERR_CUDA = 2,      /* a CUDA runtime/driver call failed (message has the CUDA error)    */
+  TT_ERR_WORKSPACE = 3, /* workspace too small                                               */
+  TT_ERR_UNSUPPORTED = 4
+};
+
+/* ABI version of the loaded library (== TT_B200_ABI_VERSION of the header it was built from). */
+int tt_abi_version(void);
+
+/* Thread-local message describing the last non-zero return on this thread ("" if none). */
+const char* tt_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Buyer tower pooling  (reference: src/models/buyer_tower.py)
+ * ------------------------------------------------------------------------------------------
+ * x      f32 [B,S,D] row-major, D fastest          (dense variant)
+ * table  f32 [N,D], idx i64 [B,S]                  (gather variant: row s of buyer b is
+ *                                                   table[idx[b,s]]; idx < 0 or >= N reads as
+ *                                                   an all-zero row, i.e. the reference's
+ *                                                   zero-padded history, trainer.py:144-151)
+ * w      f32 [B,S]   event weights (arbitrary floats; zeros allowed)
+ * out    f32 [B,D]   L2-normalised buyer embeddings
+ *
+ * weighted_avg (buyer_tower.py:58-66):
+ *     nw = w / (sum_s w + 1e-8);  y = sum_s x_s * nw_s;  out = y / max(||y||_2, 1e-12)
+ * attention (buyer_tower.py:85-99), given logit_s = W2 . relu(W1 x_s + b1) + b2:
+ *     c = logit * w;  a = softmax_s(c);  y = sum_s x_s * a_s;  out = y / max(||y||_2, 1e-12)
+ *     (no masking: a zero-weight position keeps softmax mass e^0, exactly as the reference)
+ */
+int tt_pool_weighted(const float* x, const float* w, float* out,
+                     int B, int S, int D, void* stream);
+
+int tt_pool_weighted_gather(const float* table, int64_t N, const int64_t* idx, const float* w,
+                            float* out, int B, int S, int D, void* stream);
+
+/* logits[r] = W2 . relu(W1 x_r + b1) + b2 for R rows of x (fp32 FMA arithmetic throughout).
+ * x f32 [R,D], W1 f32 [H,D], b1 f32 [H], W2 f32 [H], b2 f32 [1], logits f32 [R].
+ * (buyer_tower.py:32-36 and :85-86).  For the gather path call it once over the item table
+ * (R = N) and keep the result: the logit depends on the item row only. */
+int tt_attention_logits(const float* x, int64_t R, int D,
+                        const float* W1, const float* b1, const float* W2, const float* b2,
+                        int H, float* logits, void* stream);
+
+/* Softmax-weighted pooling with precomputed logits.  logits f32 [B,S] (dense) or f32 [N]
+ * indexed through idx (gather; an out-of-range idx has logit b2-less 0 row semantics: the
+ * caller passes zero_row_logit = W2.relu(b1)+b2, the logit of an all-zero row). */
+int tt_pool_attention(const float* x, const float* logits, const float* w, float* out,
+                      int B, int S, int D, void* stream);
+
+int tt_pool_attention_gather(const float* table, int64_t N, const float* row_logits,
+                             float zero_row_logit, const int64_t* idx, const float* w,
+                             float* out, int B, int S, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Exact inner-product index  (reference: src/inference/vector_db.py over faiss.IndexFlatIP)
+ * ------------------------------------------------------------------------------------------
+ * The index is two device arrays owned by the caller:
+ *   Xn  f32  [N, D]            rows x / (||x||_2 + 1e-8)              (vector_db.py:44-45,51)
+ *   Xh  bf16 [N, Dp]           round-to-nearest-even of Xn, row pitch Dp = tt_flat_pitch(D),
+ *                              zero padded; the copy the tensor-core scan streams
+ * plus stats f32 [4] = { max_row ||bf16(xn)||, max_row ||bf16(xn) - xn||, 0, 0 }, which bound
+ * the bf16 scoring error so that the search can certify exactness per query.
+ */
+int64_t tt_flat_pitch(int D); /* D rounded up to a multiple of 64 (one 128-byte TMA box) */
+
+/* Add `rows` rows of X to the index arrays starting at row `row0` and fold their norms into
+ * stats (call once per chunk; zero `stats` before the first chunk).
+ *   normalize = 1 : Xn = x / (||x|| + 1e-8)          (build_index, vector_db.py:44-45)
+ *   normalize = 0 : Xn = x verbatim                   (load_index of rows faiss already stored,
+ *                                                      vector_db.py:77)
+ * Xn + row0*D may alias X (in-place). */
+int tt_flat_build(const float* X, int64_t rows, int D, int normalize,
+                  float* Xn, void* Xh, int64_t row0, float* stats, void* stream);
+
+/* Bytes of device workspace tt_flat_search needs for (N, D, nq, K). */
+size_t tt_flat_search_workspace_bytes(int64_t N, int D, int nq, int K);
+
+/* Exact top-K inner-product search of nq queries against the index.
+ *   q       f32 [nq, D]   un-normalised; the op renormalises with q / (||q|| + 1e-8)
+ *                         (vector_db.py:152-153 / :189-190)
+ *   K       1 <= K <= min(N, TT_FLAT_MAX_K)   (the caller clamps k = min(k, ntotal),
+ *                         vector_db.py:159)
+ *   scores  f32 [nq, K]   fp32 inner products, descending
+ *   ids     i64 [nq, K]   row index + id_offset; ties ordered by ascending id
+ *   flags   i32 [nq]      1 = top-K certified exact, 0 = this query must be re-run through
+ *                         tt_flat_search_exact (never observed on exchangeable data)
+ *   n_uncertified i32 [1] number of zeros in flags
+ * Scores come from a bf16 tensor-core scan (tcgen05) that over-fetches a candidate set, followed
+ * by fp32 rescoring of every candidate; the certificate proves no row outside the candidate set
+ * can belong to the fp32 top-K.  Asynchronous on `stream`. */
+#define TT_FLAT_MAX_K 2048
+int tt_flat_search(const float* q, int nq,
+                   const float* Xn, const void* Xh, const float* stats, int64_t N, int D,
+                   int K, int64_t id_offset,
+                   float* scores, int64_t* ids, int32_t* flags, int32_t* n_uncertified,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Always-exact fp32 path (CUDA-core scoring + radix select), used for uncertified queries and
+ * as an independent on-device cross-check.  qsel i32 [nsel] lists the query rows to process
+ * (NULL = all nq queries, nsel = nq); results are written to the same rows of scores/ids. */
+size_t tt_flat_search_exact_workspace_bytes(int64_t N, int D, int nsel, int K);
+int tt_flat_search_exact(const float* q, int nq, const int32_t* qsel, int nsel,
+                         const float* Xn, int64_t N, int D, int K, int64_t id_offset,
+                         float* scores, int64_t* ids,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Merge G per-shard sorted top-K lists into one: scores_g f32 [G, nq, K], ids_g i64 [G, nq, K]
+ * (the layout an all-gather of per-rank [nq,K] results produces) -> [nq, K], same ordering
+ * (score descending, id ascending). */
+int tt_topk_merge(const float* scores_g, const int64_t* ids_g, int G, int nq, int K,
+                  float* scores, int64_t* ids, void* stream);
+
+/* Diagnostic / parity-test entry: the raw bf16 tensor-core scores of EVERY row of a small catalog
+ * (N <= 2^22), out f32 [nq, N] = <bf16(qn), Xh[r]> with fp32 accumulation, as the scan kernel's
+ * epilogue sees them.  Runs the same kernel as tt_flat_search with the threshold at -inf. */
+size_t tt_flat_scan_scores_workspace_bytes(int64_t N, int D, int nq);
+int tt_flat_scan_scores(const float* q, int nq, const void* Xh, const float* stats, int64_t N, int D,
+                        float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_B200_H_ */

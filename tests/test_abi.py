@@ -1,0 +1,59 @@
+"""CPU: the C-ABI library loads and exports exactly what include/tt_b200.h declares."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "tt_b200.h"
+
+
+def declared_functions():
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_surface():
+    names = declared_functions()
+    for n in ["tt_pool_weighted", "tt_pool_weighted_gather", "tt_attention_logits", "tt_pool_attention",
+              "tt_pool_attention_gather", "tt_flat_build", "tt_flat_search", "tt_flat_search_exact", "tt_topk_merge",
+              "tt_flat_search_workspace_bytes", "tt_last_error", "tt_abi_version"]:
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    for name in declared_functions():
+        assert hasattr(native_lib, name), f"{name} declared in include/tt_b200.h but not exported"
+
+
+def test_binding_covers_header(native_lib):
+    from two_tower_model_v2_b200 import _native
+    assert sorted(_native.SIGNATURES) == declared_functions()
+    assert native_lib.tt_abi_version() == _native.ABI_VERSION
+
+
+def test_argument_errors_are_reported_without_a_gpu(native_lib):
+    from two_tower_model_v2_b200 import _native
+    rc = native_lib.tt_pool_weighted(None, None, None, 1, 1, 1, None)
+    assert rc == 1 and "null pointer" in _native.last_error()
+    with pytest.raises(ValueError):
+        _native.check(rc, "tt_pool_weighted")
+    assert native_lib.tt_flat_pitch(384) == 384 and native_lib.tt_flat_pitch(100) == 128
+    assert native_lib.tt_flat_search_workspace_bytes(10_000_000, 384, 128, 100) > 0
+    assert native_lib.tt_flat_search_workspace_bytes(0, 384, 1, 1) == 0
+
+
+def test_sass_is_blackwell_native():
+    """The scan kernel must contain tcgen05 MMA / TMEM loads / TMA loads (SASS: UTCHMMA, LDTM, UTMALDG)."""
+    import shutil
+    import subprocess
+    from two_tower_model_v2_b200 import _native
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", str(_native.LIB_PATH)], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, f"{mnemonic} missing from SASS"
+    assert "HMMA.16" not in sass, "legacy mma.sync path found"

@@ -1,0 +1,200 @@
+"""GPU: exact inner-product search through the C-ABI vs the CPU oracle (seeded), the golden vectors
+of the reference wrapper, and size-independent properties at the BASELINE 1M x 384 size."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden
+from oracle import flat_ip_oracle as fo
+
+pytestmark = pytest.mark.gpu
+VDB_CASES = sorted(p.name for p in GOLDEN.glob("vector_db_*.npz"))
+
+
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def build(x):
+    import two_tower_model_v2_b200 as pkg
+    idx = pkg.FlatIPIndex(x.shape[1])
+    idx.add(x)
+    return idx
+
+
+def check(idx, x, q, k, expect_certified=True):
+    qd = torch.from_numpy(q).to(dev())
+    scores, ids, flags, nunc = idx.search_device(qd, k)
+    n_bad = int(nunc.item())
+    if n_bad:
+        qsel = torch.nonzero(flags == 0).flatten().to(torch.int32)
+        idx.search_exact_device(qd, k, scores, ids, qsel)
+    xn, qn = fo.normalize_rows(x), fo.normalize_rows(q)
+    rs, ri = fo.search(xn, qn, k)
+    ok, msg = fo.compare_topk(scores.cpu().numpy(), ids.cpu().numpy(), rs, ri, xn, qn)
+    assert ok, msg
+    if expect_certified:
+        assert n_bad == 0, f"{n_bad}/{q.shape[0]} queries were not certified by the tensor-core path"
+    return n_bad
+
+
+# ---- the scan kernel itself: raw bf16 tensor-core scores vs the same arithmetic in torch ----------
+@pytest.mark.parametrize("N,D,nq", [(256, 64, 128), (1000, 64, 5), (2048, 384, 128), (5000, 384, 1),
+                                      (3000, 384, 200), (1500, 100, 70), (4096, 768, 64), (2000, 768, 100),
+                                      (777, 512, 33), (1000, 1024, 64)])
+def test_scan_scores_match_bf16_reference(N, D, nq):
+    rng = np.random.default_rng(N + D + nq)
+    x = rng.standard_normal((N, D)).astype(np.float32)
+    q = rng.standard_normal((nq, D)).astype(np.float32)
+    idx = build(x)
+    got = idx.scan_scores_device(torch.from_numpy(q).to(dev()))
+    xh = idx.xh[:, :D].float()
+    qn = torch.from_numpy(fo.normalize_rows(q)).to(dev())
+    ref = (qn.to(torch.bfloat16).float().double() @ xh.double().T).float()
+    assert not torch.isnan(got).any(), "the scan did not report every row"
+    assert (got - ref).abs().max().item() < 2e-5   # fp32 accumulation-order noise only
+    # stored rows: fp32 normalised copy and its bf16 rounding
+    xn = fo.normalize_rows(x)
+    assert np.abs(idx.xn.cpu().numpy() - xn).max() < 1e-6
+    assert torch.equal(idx.xh[:, :D], idx.xn.to(torch.bfloat16))
+    assert idx.xh[:, D:].abs().sum().item() == 0
+
+
+@pytest.mark.parametrize("N,D,nq,k", [
+    (20000, 384, 64, 10),      # C1 catalog / k
+    (20000, 384, 2000, 10),    # C1 full query count (16 query blocks)
+    (100000, 384, 1, 100), (100000, 384, 7, 100), (100000, 384, 129, 100), (50000, 384, 300, 1),
+    (30000, 768, 50, 100),     # C4 width (M=64 path)
+    (30000, 100, 33, 37),      # D not a multiple of 64
+    (9000, 64, 16, 1000),      # API maximum k (server.py:46)
+    (70000, 256, 40, 500),
+])
+def test_search_matches_oracle(N, D, nq, k):
+    rng = np.random.default_rng(N + nq + k)
+    x = (rng.standard_normal((N, D)) * rng.uniform(0.2, 2.0, (N, 1))).astype(np.float32)
+    q = rng.standard_normal((nq, D)).astype(np.float32)
+    check(build(x), x, q, k)
+
+
+@pytest.mark.parametrize("N,k", [(1, 1), (7, 7), (100, 10), (300, 300), (2048, 100), (2049, 100), (5000, 1000)])
+def test_small_catalogs(N, k):
+    rng = np.random.default_rng(N)
+    x = rng.standard_normal((N, 32)).astype(np.float32)
+    q = rng.standard_normal((9, 32)).astype(np.float32)
+    check(build(x), x, q, k)
+
+
+def test_duplicates_and_ties():
+    """Duplicate rows tie exactly; ids inside a tie may differ from the oracle but must be valid, and our
+    own order is (score desc, id asc)."""
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((500, 384)).astype(np.float32)
+    x = np.concatenate([base] * 40)                      # every row appears 40 times
+    q = base[:16] + 0.01 * rng.standard_normal((16, 384)).astype(np.float32)
+    idx = build(x)
+    check(idx, x, q, 100, expect_certified=False)
+    s, i, _ = idx.search_checked_device(torch.from_numpy(q).to(dev()), 100)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    for r in range(16):
+        for a in range(99):
+            assert s[r, a] > s[r, a + 1] or (s[r, a] == s[r, a + 1] and i[r, a] < i[r, a + 1])
+    assert np.array_equal(i[:, :40] % 500, np.repeat(np.arange(16)[:, None], 40, 1))
+
+
+def test_clustered_catalog_falls_back_exactly():
+    """A catalog ordered by cluster defeats the sampled threshold for some queries; the certificate must
+    catch it and the exact path must repair it."""
+    rng = np.random.default_rng(4)
+    centers = rng.standard_normal((50, 384)).astype(np.float32)
+    x = np.repeat(centers, 2000, axis=0) + 0.05 * rng.standard_normal((100000, 384)).astype(np.float32)
+    q = centers[:32] + 0.05 * rng.standard_normal((32, 384)).astype(np.float32)
+    check(build(x), x, q, 100, expect_certified=False)
+
+
+def test_exact_path_alone():
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((40000, 384)).astype(np.float32)
+    q = rng.standard_normal((19, 384)).astype(np.float32)
+    idx = build(x)
+    s, i = idx.search_exact_device(torch.from_numpy(q).to(dev()), 100)
+    xn, qn = fo.normalize_rows(x), fo.normalize_rows(q)
+    rs, ri = fo.search(xn, qn, 100)
+    ok, msg = fo.compare_topk(s.cpu().numpy(), i.cpu().numpy(), rs, ri, xn, qn)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("case", VDB_CASES)
+def test_vector_database_matches_reference_wrapper(case, tmp_path):
+    import two_tower_model_v2_b200 as pkg
+    g = golden(case)
+    N, D = g["x"].shape
+    pids = [f"p{i:05d}" for i in range(N)]
+    db = pkg.VectorDatabase(embedding_dim=D)
+    db.build_index(g["x"], pids)
+    assert db.index.ntotal == N and db.id_to_index["p00003"] == 3 and db.index_to_id[3] == "p00003"
+    k = int(g["k"])
+    batch = db.retrieve_batch(g["q"], k)
+    ids = np.array([[int(p[1:]) for p, _ in row] for row in batch])
+    sc = np.array([[s for _, s in row] for row in batch], np.float32)
+    assert ids.shape == g["batch_ids"].shape              # k = min(k, ntotal) clamp (vector_db.py:159)
+    ok, msg = fo.compare_topk(sc, ids, g["batch_scores"], g["batch_ids"], fo.normalize_rows(g["x"]), fo.normalize_rows(g["q"]))
+    assert ok, msg
+    single = db.retrieve(g["q"][0], k)                    # 1-D query
+    assert [int(p[1:]) for p, _ in single] == ids[0].tolist() and all(isinstance(s, float) for _, s in single)
+    multi = db.retrieve(g["q"][:3], k)                    # [3,D] query: only row 0 comes back (vector_db.py:164)
+    assert [p for p, _ in multi] == [p for p, _ in single]
+    # save / load round trip through the faiss flat-file layout
+    p_idx, p_ids, p_map = tmp_path / "product_index.faiss", tmp_path / "product_ids.npy", tmp_path / "product_id_to_index.json"
+    db.save_index(str(p_idx), str(p_ids), str(p_map))
+    db2 = pkg.VectorDatabase(embedding_dim=D)
+    db2.load_index(str(p_idx), str(p_ids), str(p_map))
+    assert db2.product_ids == pids and db2.index.ntotal == N
+    assert db2.retrieve_batch(g["q"], k) == batch
+    db3 = pkg.VectorDatabase(embedding_dim=D)
+    db3.load_index(str(p_idx))                            # ids default to product_{i} (vector_db.py:84-86)
+    assert db3.product_ids[5] == "product_5"
+
+
+def test_topk_merge_matches_numpy():
+    from two_tower_model_v2_b200 import ops
+    rng = np.random.default_rng(2)
+    G, nq, K = 8, 37, 100
+    s = -np.sort(-rng.standard_normal((G, nq, K)).astype(np.float32), axis=2)
+    s[3, :, 50:] = s[2, :, 50:]                            # cross-shard ties
+    i = rng.permutation(G * nq * K).reshape(G, nq, K).astype(np.int64)
+    s[5, 0, 90:], i[5, 0, 90:] = -np.inf, -1               # a short shard list
+    ms, mi = ops.topk_merge(torch.from_numpy(s).to(dev()), torch.from_numpy(i).to(dev()))
+    flat_s = s.transpose(1, 0, 2).reshape(nq, G * K)
+    flat_i = i.transpose(1, 0, 2).reshape(nq, G * K)
+    for r in range(nq):
+        order = np.lexsort((flat_i[r], -flat_s[r]))[:K]
+        assert np.array_equal(ms[r].cpu().numpy(), flat_s[r][order])
+        assert np.array_equal(mi[r].cpu().numpy(), flat_i[r][order])
+
+
+def test_1m_catalog_properties():
+    """BASELINE config C3 size (1M x 384, k=100): every catalog row queried against the index finds itself
+    first with score ~1, lists are sorted, everything is certified, and a sampled subset of queries
+    matches the fp32 oracle."""
+    import two_tower_model_v2_b200 as pkg
+    N, D, k = 1_000_000, 384, 100
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn((N, D), device=dev(), generator=g)
+    idx = pkg.FlatIPIndex.adopt(x)
+    rows = torch.arange(0, N, 3907, device=dev())[:256]
+    q = idx.xn[rows] * 2.5                                  # un-normalised copies of stored rows
+    s, i, flags, nunc = idx.search_device(q, k)
+    assert int(nunc.item()) == 0
+    assert torch.equal(i[:, 0], rows) and (s[:, 0] - 1).abs().max() < 1e-5
+    assert (s[:, 1:] <= s[:, :-1]).all()
+    for nq in (1, 128, 1024):
+        qr = torch.randn((nq, D), device=dev(), generator=g)
+        s, i, flags, nunc = idx.search_device(qr, k)
+        assert int(nunc.item()) == 0 and (s[:, 1:] <= s[:, :-1]).all()
+        sub = slice(0, min(nq, 4))
+        xn = idx.xn.cpu().numpy()
+        qn = fo.normalize_rows(qr[sub].cpu().numpy())
+        rs, ri = fo.search(xn, qn, k, block=1 << 18)
+        ok, msg = fo.compare_topk(s[sub].cpu().numpy(), i[sub].cpu().numpy(), rs, ri, xn, qn)
+        assert ok, msg

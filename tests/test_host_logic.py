@@ -1,0 +1,90 @@
+"""CPU: host-side logic of the drop-in classes (no compute calls)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import two_tower_model_v2_b200 as pkg
+from two_tower_model_v2_b200.vector_db import read_flat_ip_file, write_flat_ip_file
+
+
+def test_buyer_tower_constructor_and_state_dict():
+    m = pkg.BuyerTower()                      # defaults: 384, attention, 128 (buyer_tower.py:14-16)
+    assert m.embedding_dim == 384 and m.aggregation_method == "attention"
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "attention.0.weight": (128, 384), "attention.0.bias": (128,),
+        "attention.2.weight": (1, 128), "attention.2.bias": (1,)}
+    assert sum(v.numel() for v in sd.values()) == 49409
+    assert len(pkg.BuyerTower(384, "weighted_avg").state_dict()) == 0
+    with pytest.raises(ValueError, match="Unknown aggregation method: nope"):
+        pkg.BuyerTower(384, "nope")
+    m.aggregation_method = "nope"             # forward re-checks (buyer_tower.py:122)
+    with pytest.raises(ValueError, match="Unknown aggregation method"):
+        m(torch.zeros(1, 1, 384), torch.zeros(1, 1))
+
+
+def test_buyer_tower_loads_reference_style_checkpoint():
+    sd = {"attention.0.weight": torch.randn(128, 384), "attention.0.bias": torch.randn(128),
+          "attention.2.weight": torch.randn(1, 128), "attention.2.bias": torch.randn(1)}
+    m = pkg.BuyerTower()
+    m.load_state_dict(sd, strict=True)
+    assert torch.equal(m.attention[0].weight, sd["attention.0.weight"])
+
+
+def test_buyer_tower_has_no_cpu_fallback():
+    m = pkg.BuyerTower(8, "weighted_avg")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(2, 3, 8), torch.ones(2, 3))
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 3, 8), torch.ones(2, 4))
+
+
+def test_vector_database_errors_match_reference():
+    db = pkg.VectorDatabase(embedding_dim=16)
+    assert db.index is None and db.product_ids is None and db.id_to_index is None and db.index_to_id is None
+    with pytest.raises(ValueError, match="Embedding dimension mismatch: expected 16, got 8"):
+        db.build_index(np.zeros((4, 8), np.float32), ["a", "b", "c", "d"])
+    with pytest.raises(ValueError, match="Index not built"):
+        db.retrieve(np.zeros(16, np.float32))
+    with pytest.raises(ValueError, match="Index not built"):
+        db.retrieve_batch(np.zeros((2, 16), np.float32))
+    with pytest.raises(ValueError, match="Index not built"):
+        db.save_index("/tmp/nope.faiss")
+    assert db.get_embedding("x") is None
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            db.build_index(np.zeros((4, 16), np.float32), ["a", "b", "c", "d"])
+
+
+def test_flat_file_round_trip(tmp_path):
+    rows = np.random.default_rng(0).standard_normal((37, 12)).astype(np.float32)
+    p = tmp_path / "product_index.faiss"
+    write_flat_ip_file(str(p), rows)
+    raw = p.read_bytes()
+    assert raw[:4] == b"IxFI" and len(raw) == 45 + rows.nbytes
+    assert np.array_equal(read_flat_ip_file(str(p)), rows)
+    p.write_bytes(b"IxF2" + raw[4:])
+    with pytest.raises(ValueError, match="not an IndexFlatIP"):
+        read_flat_ip_file(str(p))
+    p.write_bytes(raw[:-4])
+    with pytest.raises(ValueError, match="truncated"):
+        read_flat_ip_file(str(p))
+
+
+def test_event_weights():
+    cfg = {"event_weights": {"view": 1, "add_to_cart": 5, "purchase": 10}}
+    got = [pkg.get_event_weight(e, cfg) for e in ("View", "AddToCart", "add_to_cart", "Purchase", "BUY", "wishlist")]
+    assert got == [1, 5, 5, 10, 10, 1]
+    assert pkg.get_event_weight("purchase", {}) == 1
+
+
+def test_shard_bounds_cover_catalog():
+    for n, g in [(10, 4), (10_000_000, 8), (7, 8), (0, 2), (100, 1)]:
+        spans = [pkg.shard_bounds(n, g, r) for r in range(g)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(0 <= hi - lo <= -(-n // g) for lo, hi in spans)
+    with pytest.raises(ValueError):
+        pkg.shard_bounds(10, 2, 2)

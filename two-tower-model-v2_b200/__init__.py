@@ -1,0 +1,19 @@
+"""B200-native serving hot path of the two-tower recommender (HeikalPro/two-tower-model-v2).
+
+Drop-in replacements for the reference's two hot-path modules, backed by hand-written sm_100a
+CUDA kernels behind the C-ABI in include/tt_b200.h:
+
+    reference                              here
+    src/models/buyer_tower.BuyerTower      two_tower_model_v2_b200.BuyerTower
+    src/inference/vector_db.VectorDatabase two_tower_model_v2_b200.VectorDatabase
+
+The directory is named `two-tower-model-v2_b200`; import it as `two_tower_model_v2_b200`
+(the root-level `two_tower_model_v2_b200.py` aliases it).
+"""
+from .buyer_tower import BuyerTower
+from .config import get_event_weight
+from .sharded import ShardedFlatIPIndex, shard_bounds
+from .vector_db import FlatIPIndex, VectorDatabase, read_flat_ip_file, write_flat_ip_file
+
+__all__ = ["BuyerTower", "VectorDatabase", "FlatIPIndex", "ShardedFlatIPIndex", "shard_bounds",
+           "get_event_weight", "read_flat_ip_file", "write_flat_ip_file"]

@@ -1,0 +1,126 @@
+// C-ABI glue: error reporting and the tt_flat_search orchestration (include/tt_b200.h).
+#include "tt_common.cuh"
+#include "flat_internal.cuh"
+
+namespace tt {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+struct SearchWs {
+  size_t qn, qh, eps, thr, cnt, cand, sample, total;
+};
+
+static SearchWs search_ws_layout(const ScanPlan& pl, int D, int nq) {
+  SearchWs w{};
+  size_t o = 0;
+  w.qn = o;     o += align_up((size_t)nq * D * sizeof(float), 256);
+  w.qh = o;     o += align_up((size_t)pl.nq_pad * pl.Dp * 2, 256);
+  w.eps = o;    o += align_up((size_t)nq * sizeof(float), 256);
+  w.thr = o;    o += align_up((size_t)nq * sizeof(float), 256);
+  w.cnt = o;    o += align_up((size_t)nq * sizeof(unsigned int), 256);
+  w.cand = o;   o += align_up((size_t)nq * pl.cand_cap * 8, 256);
+  w.sample = o; o += align_up((size_t)pl.sample_slices * pl.nq_pad * SAMPLE_R * sizeof(float), 256);
+  w.total = o;
+  return w;
+}
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" __attribute__((visibility("default"))) int tt_abi_version(void) { return TT_B200_ABI_VERSION; }
+extern "C" __attribute__((visibility("default"))) const char* tt_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" __attribute__((visibility("default"))) size_t tt_flat_search_workspace_bytes(int64_t N, int D, int nq, int K) {
+  if (N < 1 || D < 1 || nq < 1 || K < 1) return 0;
+  const ScanPlan pl = make_scan_plan(N, D, nq, K);
+  return search_ws_layout(pl, D, nq).total;
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_flat_search(const float* q, int nq, const float* Xn, const void* Xh, const float* stats,
+                              int64_t N, int D, int K, int64_t id_offset, float* scores, int64_t* ids,
+                              int32_t* flags, int32_t* n_uncertified, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  TT_CHECK_ARG(q && Xn && Xh && stats && scores && ids && flags && n_uncertified, "null pointer");
+  TT_CHECK_ARG(nq >= 0, "nq < 0");
+  TT_CHECK_ARG(N >= 1 && N < (1LL << 31), "need 1 <= N < 2^31 rows per shard");
+  TT_CHECK_ARG(D >= 1, "D < 1");
+  TT_CHECK_ARG(K >= 1 && K <= N && K <= TT_FLAT_MAX_K, "need 1 <= K <= min(N, TT_FLAT_MAX_K)");
+  TT_CHECK_ARG((reinterpret_cast<uintptr_t>(Xh) & 15) == 0, "Xh must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  TT_CHECK_CUDA(cudaMemsetAsync(n_uncertified, 0, sizeof(int32_t), st));
+  if (nq == 0) return TT_OK;
+
+  const ScanPlan pl = make_scan_plan(N, D, nq, K);
+  if (!pl.supported) {
+    set_error("tt_flat_search: embedding dimension too large for the resident-query scan (D <= 1024 supported)");
+    return TT_ERR_UNSUPPORTED;
+  }
+  const SearchWs w = search_ws_layout(pl, D, nq);
+  TT_CHECK_ARG(workspace != nullptr, "null workspace");
+  if (workspace_bytes < w.total) { set_error("tt_flat_search: workspace too small"); return TT_ERR_WORKSPACE; }
+  TT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  float* qn = reinterpret_cast<float*>(ws + w.qn);
+  void* qh = ws + w.qh;
+  float* eps = reinterpret_cast<float*>(ws + w.eps);
+  float* thr = reinterpret_cast<float*>(ws + w.thr);
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(ws + w.cnt);
+  void* cand = ws + w.cand;
+  float* sample = reinterpret_cast<float*>(ws + w.sample);
+
+  TT_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(unsigned int), st));
+  if (int e = launch_prep_queries(q, nq, pl.nq_pad, D, pl.Dp, stats, qn, qh, eps, st)) return e;
+  if (int e = launch_scan(pl, qh, Xh, N, nq, thr, cnt, cand, sample, st)) return e;
+  return launch_finalize(pl, qn, Xn, N, D, nq, K, id_offset, thr, eps, cnt, cand, scores,
+                         reinterpret_cast<long long*>(ids), flags, n_uncertified, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Diagnostic: dense bf16 tensor-core scores of a small catalog (parity tests of the scan itself).
+namespace tt {
+__global__ void scatter_scores_kernel(const unsigned int* __restrict__ cnt, const uint2* __restrict__ cand,
+                                      int cap, long long N, float* __restrict__ out) {
+  const int q = blockIdx.y;
+  const unsigned int n = min(cnt[q], (unsigned int)cap);
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint2 c = cand[(size_t)q * cap + i];
+    if ((long long)c.y < N) out[(long long)q * N + c.y] = __uint_as_float(c.x);
+  }
+}
+}  // namespace tt
+
+extern "C" __attribute__((visibility("default"))) size_t tt_flat_scan_scores_workspace_bytes(int64_t N, int D, int nq) {
+  if (N < 1 || D < 1 || nq < 1) return 0;
+  ScanPlan pl = make_scan_plan(N, D, nq, 1);
+  pl.use_threshold = false;
+  pl.cand_cap = (int)N;
+  return search_ws_layout(pl, D, nq).total;
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_flat_scan_scores(const float* q, int nq, const void* Xh, const float* stats, int64_t N, int D,
+                                   float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  TT_CHECK_ARG(q && Xh && stats && out && workspace, "null pointer");
+  TT_CHECK_ARG(nq >= 1 && N >= 1 && N <= (1 << 22) && D >= 1, "need nq >= 1, 1 <= N <= 2^22, D >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  ScanPlan pl = make_scan_plan(N, D, nq, 1);
+  if (!pl.supported) { set_error("tt_flat_scan_scores: D too large"); return TT_ERR_UNSUPPORTED; }
+  pl.use_threshold = false;
+  pl.cand_cap = (int)N;
+  const SearchWs w = search_ws_layout(pl, D, nq);
+  if (workspace_bytes < w.total) { set_error("tt_flat_scan_scores: workspace too small"); return TT_ERR_WORKSPACE; }
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  float* qn = reinterpret_cast<float*>(ws + w.qn);
+  void* qh = ws + w.qh;
+  float* eps = reinterpret_cast<float*>(ws + w.eps);
+  float* thr = reinterpret_cast<float*>(ws + w.thr);
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(ws + w.cnt);
+  void* cand = ws + w.cand;
+  float* sample = reinterpret_cast<float*>(ws + w.sample);
+  TT_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(unsigned int), st));
+  TT_CHECK_CUDA(cudaMemsetAsync(out, 0xFF, (size_t)nq * N * sizeof(float), st));   // NaN = "row never reported"
+  if (int e = launch_prep_queries(q, nq, pl.nq_pad, D, pl.Dp, stats, qn, qh, eps, st)) return e;
+  if (int e = launch_scan(pl, qh, Xh, N, nq, thr, cnt, cand, sample, st)) return e;
+  scatter_scores_kernel<<<dim3(64, nq), 256, 0, st>>>(cnt, reinterpret_cast<const uint2*>(cand), pl.cand_cap, N, out);
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}

@@ -1,0 +1,186 @@
+// Attention-score MLP of the buyer tower (reference: src/models/buyer_tower.py:32-36,85-86):
+//     logit[r] = W2 . relu(W1 x_r + b1) + b2
+// fp32 FMA arithmetic end to end.  A bf16 tensor-core MLP does NOT meet the 1e-5 tolerance of
+// the pooled output (the event weight, up to 10, multiplies the logit inside exp; measured
+// 4e-4), so this is a register-tiled CUDA-core SGEMM with the ReLU / W2 dot / bias fused into
+// the epilogue: the [R,H] hidden activations never leave registers.
+// Roofline: fp32 FMA pipe, 2*D*H + 2*H flop per row.
+#include "tt_common.cuh"
+
+namespace tt {
+
+constexpr int AL_BM = 128;     // rows per CTA tile
+constexpr int AL_BN = 128;     // hidden units per chunk
+constexpr int AL_BK = 32;      // k-slab
+constexpr int AL_LD = AL_BK + 4;   // padded smem row (floats): conflict-free 128-bit LDS/STS
+constexpr int AL_THREADS = 256;
+constexpr int AL_STAGE_FLOATS = (AL_BM + AL_BN) * AL_LD;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// Loads one k-slab of the X tile and of the W1 chunk into a stage (zero-filling out-of-range
+// rows / hidden units / k).
+__device__ __forceinline__ void al_load_stage(float* stage, const float* __restrict__ x, long long R, int D,
+                                              const float* __restrict__ W1, int H,
+                                              long long row0, int h0, int k0, int tid) {
+  float* Xs = stage;
+  float* Ws = stage + AL_BM * AL_LD;
+#pragma unroll
+  for (int i = 0; i < (AL_BM * AL_BK / 4) / AL_THREADS; ++i) {
+    const int f = tid + i * AL_THREADS;
+    const int r = f >> 3, c4 = f & 7;
+    const long long gr = row0 + r;
+    const int k = k0 + c4 * 4;
+    const bool ok = (gr < R) && (k < D);
+    cp_async16(Xs + r * AL_LD + c4 * 4, ok ? (x + gr * D + k) : x, ok ? 16 : 0);
+  }
+#pragma unroll
+  for (int i = 0; i < (AL_BN * AL_BK / 4) / AL_THREADS; ++i) {
+    const int f = tid + i * AL_THREADS;
+    const int r = f >> 3, c4 = f & 7;
+    const int gh = h0 + r;
+    const int k = k0 + c4 * 4;
+    const bool ok = (gh < H) && (k < D);
+    cp_async16(Ws + r * AL_LD + c4 * 4, ok ? (W1 + (long long)gh * D + k) : W1, ok ? 16 : 0);
+  }
+}
+
+__global__ void __launch_bounds__(AL_THREADS, 2)
+attn_logits_kernel(const float* __restrict__ x, long long R, int D,
+                   const float* __restrict__ W1, const float* __restrict__ b1,
+                   const float* __restrict__ W2, const float* __restrict__ b2, int H,
+                   float* __restrict__ logits) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15;    // hidden sub-index: hidden = h0 + tx + 16*j
+  const int ty = tid >> 4;    // row sub-index:    row    = row0 + ty + 16*i
+  const long long row0 = (long long)blockIdx.x * AL_BM;
+  const int nk = (D + AL_BK - 1) / AL_BK;
+
+  float logit[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) logit[i] = 0.f;
+
+  for (int h0 = 0; h0 < H; h0 += AL_BN) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    al_load_stage(smem, x, R, D, W1, H, row0, h0, 0, tid);
+    cp_async_commit();
+    for (int kt = 0; kt < nk; ++kt) {
+      float* cur = smem + (kt & 1) * AL_STAGE_FLOATS;
+      if (kt + 1 < nk) {
+        al_load_stage(smem + ((kt + 1) & 1) * AL_STAGE_FLOATS, x, R, D, W1, H, row0, h0, (kt + 1) * AL_BK, tid);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const float* Xs = cur;
+      const float* Ws = cur + AL_BM * AL_LD;
+#pragma unroll
+      for (int kk4 = 0; kk4 < AL_BK / 4; ++kk4) {
+        float4 xa[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          xa[i] = *reinterpret_cast<const float4*>(Xs + (ty + 16 * i) * AL_LD + kk4 * 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 wb = *reinterpret_cast<const float4*>(Ws + (tx + 16 * j) * AL_LD + kk4 * 4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a = acc[i][j];
+            a = fmaf(xa[i].x, wb.x, a);
+            a = fmaf(xa[i].y, wb.y, a);
+            a = fmaf(xa[i].z, wb.z, a);
+            a = fmaf(xa[i].w, wb.w, a);
+            acc[i][j] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // fused epilogue for this hidden chunk: relu(acc + b1) . W2
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int h = h0 + tx + 16 * j;
+      const float bj = (h < H) ? __ldg(b1 + h) : 0.f;
+      const float wj = (h < H) ? __ldg(W2 + h) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) logit[i] = fmaf(fmaxf(acc[i][j] + bj, 0.f), wj, logit[i]);
+    }
+  }
+  const float bias2 = __ldg(b2);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float v = logit[i];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    const long long r = row0 + ty + 16 * i;
+    if (tx == 0 && r < R) logits[r] = v + bias2;
+  }
+}
+
+// Shapes the tiled kernel does not take (D % 4 != 0 or unaligned pointers): one CTA per row.
+__global__ void __launch_bounds__(128)
+attn_logits_generic_kernel(const float* __restrict__ x, long long R, int D,
+                           const float* __restrict__ W1, const float* __restrict__ b1,
+                           const float* __restrict__ W2, const float* __restrict__ b2, int H,
+                           float* __restrict__ logits) {
+  extern __shared__ float xs[];
+  __shared__ float red[4];
+  const long long r = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = x[r * D + d];
+  __syncthreads();
+  float part = 0.f;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float a = 0.f;
+    const float* wr = W1 + (long long)h * D;
+    for (int d = 0; d < D; ++d) a = fmaf(xs[d], __ldg(wr + d), a);
+    part = fmaf(fmaxf(a + __ldg(b1 + h), 0.f), __ldg(W2 + h), part);
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) logits[r] = red[0] + red[1] + red[2] + red[3] + __ldg(b2);
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" __attribute__((visibility("default"))) int tt_attention_logits(const float* x, int64_t R, int D,
+                                   const float* W1, const float* b1, const float* W2, const float* b2,
+                                   int H, float* logits, void* stream) {
+  TT_CHECK_ARG(x && W1 && b1 && W2 && b2 && logits, "null pointer");
+  TT_CHECK_ARG(R >= 0 && D >= 1 && H >= 1, "need R >= 0, D >= 1, H >= 1");
+  if (R == 0) return TT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fast = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(W1) & 15) == 0);
+  if (fast) {
+    const size_t smem = 2 * AL_STAGE_FLOATS * sizeof(float);
+    TT_CHECK_CUDA(cudaFuncSetAttribute(attn_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (R + AL_BM - 1) / AL_BM;
+    TT_CHECK_ARG(grid <= 0x7fffffffLL, "too many rows");
+    attn_logits_kernel<<<(unsigned)grid, AL_THREADS, smem, st>>>(x, R, D, W1, b1, W2, b2, H, logits);
+  } else {
+    TT_CHECK_ARG(R <= 0x7fffffffLL, "too many rows");
+    TT_CHECK_ARG((size_t)D * sizeof(float) <= 48 * 1024, "D too large for the generic logits kernel");
+    attn_logits_generic_kernel<<<(unsigned)R, 128, (size_t)D * sizeof(float), st>>>(x, R, D, W1, b1, W2, b2, H, logits);
+  }
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}

@@ -1,0 +1,40 @@
+// Internal interfaces between the translation units of the exact inner-product search.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace tt {
+
+constexpr int SAMPLE_R = 32;               // per-thread top-R kept by the sample pass
+constexpr int FINALIZE_MAX_CAND = 16384;   // candidates per query the finalize kernel can sort (128 KiB smem)
+
+// Everything the host decides about one search call (pure function of N, D, nq, K and the SM count).
+struct ScanPlan {
+  int Dp, num_kb, block_m, num_stages;
+  bool supported;
+  size_t smem_bytes;
+  int nqb, nq_pad, num_tiles;
+  int target;          // expected candidates per query
+  int cand_cap;        // capacity of a query's candidate list
+  bool use_threshold;  // false: catalog small enough that every row is a candidate
+  int main_slices;
+  int sample_stride, sample_slots, sample_slices, sample_rank;
+};
+
+ScanPlan make_scan_plan(long long N, int D, int nq, int K);
+
+int launch_prep_queries(const float* q, int nq, int nq_pad, int D, int Dp, const float* stats,
+                        float* qn, void* qh, float* eps, cudaStream_t st);
+
+// sample pass (if plan.use_threshold) + threshold selection + main scan
+int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq,
+                float* thr, unsigned int* cand_cnt, void* cand, float* sample_buf, cudaStream_t st);
+
+// fp32 rescoring of every candidate, exact sort, certificate
+int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long long N, int D, int nq, int K,
+                    long long id_offset, const float* thr, const float* eps, const unsigned int* cand_cnt,
+                    const void* cand, float* scores, long long* ids, int* flags, int* n_uncertified,
+                    cudaStream_t st);
+
+}  // namespace tt

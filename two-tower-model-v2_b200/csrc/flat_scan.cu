@@ -1,0 +1,452 @@
+// Tensor-core catalog scan with a fused candidate filter (the hot loop of
+// faiss.IndexFlatIP.search as called at src/inference/vector_db.py:160,197).
+//
+// scores[q, r] = <qh[q,:], Xh[r,:]>  (bf16 operands, fp32 accumulation in TMEM) for one block of
+// BLOCK_M queries against a stream of 256-row catalog tiles.  The score matrix never reaches
+// shared or global memory: epilogue warps read the accumulator straight out of TMEM and keep
+// only rows whose score reaches the query's threshold, appending (score, row) to a small
+// per-query candidate list in global memory (a few hundred entries for the whole catalog).
+//
+// CTA anatomy (256 threads, 1 CTA / SM):
+//   warp 0  lane 0 : TMA producer   - query block once (resident A operand, 128B swizzle),
+//                                     then catalog K-blocks [256 rows x 64 bf16] through a
+//                                     num_stages-deep mbarrier ring
+//   warp 1  lane 0 : MMA issuer     - tcgen05.mma cta_group::1 kind::f16, M=BLOCK_M, N=256, K=16;
+//                                     accumulators double-buffered in TMEM (2 x 256 columns)
+//   warp 2         : TMEM allocator
+//   warps 4-7      : epilogue       - tcgen05.ld 32x32b, one query per thread, threshold in a
+//                                     register; overlaps the next tile's MMAs
+//
+// Work decomposition: unit u = blockIdx.x -> (query block u % nqb, catalog slice u / nqb), so
+// that concurrently resident CTAs share catalog tiles through L2 when there are several query
+// blocks.
+//
+// Two epilogue modes:
+//   SAMPLE : scan every `tile_stride`-th tile and keep the per-thread top-R scores in registers;
+//            tt::select_thresholds turns them into a per-query threshold that is a guaranteed
+//            lower bound of the K-th best bf16 score (the r-th best of a subset never exceeds
+//            the r-th best of the whole).
+//   MAIN   : scan every tile, append scores >= threshold.
+#include <cuda.h>
+#include "tt_common.cuh"
+#include "sm100_ptx.cuh"
+#include "flat_internal.cuh"
+
+namespace tt {
+
+using namespace ptx;
+
+constexpr int SCAN_THREADS = 256;
+constexpr int BLOCK_N = 256;                    // catalog rows per tile
+constexpr int BLOCK_K = 64;                     // bf16 per K-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KiB
+constexpr int MAX_STAGES = 8;
+constexpr int TMEM_COLS = 512;                  // 2 accumulator buffers x 256 fp32 columns
+
+struct ScanParams {
+  long long N;            // catalog rows
+  int nq;                 // valid queries
+  int num_kb;             // K-blocks per row (Dp / 64)
+  int num_stages;         // B ring depth
+  int nqb;                // query blocks
+  int num_slots;          // tiles to visit in total (main: all tiles; sample: sampled tiles)
+  int tile_stride;        // tile index = slot * tile_stride
+  // MAIN
+  const float* thr;       // [nq]
+  unsigned int* cand_cnt; // [nq]
+  uint2* cand;            // [nq, cand_cap]  (score bits, row)
+  int cand_cap;
+  // SAMPLE
+  float* sample_out;      // [nslices, nq_pad, SAMPLE_R]
+  int nq_pad;
+};
+
+template <int BLOCK_M, bool SAMPLE>
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
+flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                 const ScanParams p) {
+  constexpr int A_KB_BYTES = BLOCK_M * BLOCK_K * 2;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled operand tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + (size_t)p.num_kb * A_KB_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.num_stages * B_STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [MAX_STAGES]
+  uint64_t* empty_bar = bars + MAX_STAGES;         // [MAX_STAGES]
+  uint64_t* a_full_bar = bars + 2 * MAX_STAGES;    // [1]
+  uint64_t* tmem_full_bar = a_full_bar + 1;        // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- work assignment ----------------------------------------------------------------------
+  const int unit = blockIdx.x;
+  const int qb = unit % p.nqb;
+  const int slice = unit / p.nqb;
+  const int nslices = gridDim.x / p.nqb;
+  const int slot_begin = (int)(((long long)p.num_slots * slice) / nslices);
+  const int slot_end = (int)(((long long)p.num_slots * (slice + 1)) / nslices);
+  const int ntiles = slot_end - slot_begin;
+
+  // ---- one-time setup -----------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_q);
+    prefetch_tensormap(&tmap_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(smem_u32(full_bar + i), 1);
+      mbar_init(smem_u32(empty_bar + i), 1);
+    }
+    mbar_init(smem_u32(a_full_bar), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(tmem_full_bar + i), 1);
+      mbar_init(smem_u32(tmem_empty_bar + i), 4);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===============================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(smem_u32(a_full_bar), (uint32_t)(p.num_kb * A_KB_BYTES));
+      for (int kb = 0; kb < p.num_kb; ++kb)
+        tma_load_2d(smem_u32(smem_a + (size_t)kb * A_KB_BYTES), &tmap_q, smem_u32(a_full_bar), kb * BLOCK_K,
+                    qb * BLOCK_M);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const long long tile = (long long)(slot_begin + t) * p.tile_stride;
+        const int row0 = (int)(tile * BLOCK_N);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1, 100 + stage);
+          mbar_arrive_expect_tx(smem_u32(full_bar + stage), B_STAGE_BYTES);
+          tma_load_2d(smem_u32(smem_b + (size_t)stage * B_STAGE_BYTES), &tmap_x, smem_u32(full_bar + stage),
+                      kb * BLOCK_K, row0);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================== MMA issuer =================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BLOCK_M, BLOCK_N);
+      const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem_a));
+      const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem_b));
+      mbar_wait(smem_u32(a_full_bar), 0, 200);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        const uint32_t use_phase = (uint32_t)(t >> 1) & 1u;
+        mbar_wait(smem_u32(tmem_empty_bar + buf), use_phase ^ 1, 210 + buf);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BLOCK_N);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(full_bar + stage), phase, 220 + stage);
+          tc_fence_after();
+          // descriptor start-address field is in 16-byte units
+          const uint64_t a_desc = a_desc0 + (uint64_t)((kb * A_KB_BYTES) >> 4);
+          const uint64_t b_desc = b_desc0 + (uint64_t)((stage * B_STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 bytes per K=16 step
+            mma_bf16_ss(d_tmem, a_desc + koff, b_desc + koff, idesc, (uint32_t)((kb | k) != 0));
+          }
+          mma_commit(smem_u32(empty_bar + stage));          // smem slot free once these MMAs retire
+          if (kb == p.num_kb - 1) mma_commit(smem_u32(tmem_full_bar + buf));
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // =========================== epilogue ====================================================
+    const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
+    int q_local;
+    if (BLOCK_M == 128) q_local = quad * 32 + lane;    // accumulator row m lives in TMEM lane m
+    else q_local = (lane < 16) ? quad * 16 + lane : -1;   // M=64: rows 16g..16g+15 -> lanes 32g..32g+15
+    const int q = qb * BLOCK_M + q_local;
+    const bool valid = (q_local >= 0) && (q < p.nq);
+
+    float thr = INFINITY;
+    float top[SAMPLE ? SAMPLE_R : 1];
+    if (SAMPLE) {
+#pragma unroll
+      for (int i = 0; i < (SAMPLE ? SAMPLE_R : 1); ++i) top[i] = -INFINITY;
+    } else {
+      if (valid) thr = __ldg(p.thr + q);
+    }
+    unsigned int* my_cnt = SAMPLE ? nullptr : (p.cand_cnt + (valid ? q : 0));
+    uint2* my_cand = SAMPLE ? nullptr : (p.cand + (size_t)(valid ? q : 0) * p.cand_cap);
+
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const uint32_t use_phase = (uint32_t)(t >> 1) & 1u;
+      const long long tile = (long long)(slot_begin + t) * p.tile_stride;
+      const long long row0 = tile * BLOCK_N;
+      const int ncols = (int)min((long long)BLOCK_N, p.N - row0);   // last tile may be partial
+      mbar_wait(smem_u32(tmem_full_bar + buf), use_phase, 300 + buf);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        if (c * 32 >= ncols) break;                    // warp-uniform
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        const int limit = ncols - c * 32;              // >= 1; columns >= limit are padding rows
+        if (SAMPLE) {
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float s = __uint_as_float(v[j]);
+              if (j < limit && s > top[SAMPLE_R - 1]) {
+#pragma unroll
+                for (int i = 0; i < SAMPLE_R; ++i) {
+                  const float hi = fmaxf(top[i], s);
+                  s = fminf(top[i], s);
+                  top[i] = hi;
+                }
+              }
+            }
+          }
+        } else {
+          float m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, (j < limit) ? __uint_as_float(v[j]) : -INFINITY);
+          if (m >= thr) {                              // rare: some column of this chunk qualifies
+            const uint32_t rbase = (uint32_t)row0 + (uint32_t)(c * 32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = __uint_as_float(v[j]);
+              if (j < limit && s >= thr) {
+                const unsigned int pos = atomicAdd(my_cnt, 1u);
+                if (pos < (unsigned int)p.cand_cap) my_cand[pos] = make_uint2(v[j], rbase + (uint32_t)j);
+              }
+            }
+          }
+        }
+      }
+      // release this accumulator buffer to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty_bar + buf));
+    }
+
+    if (SAMPLE && valid) {
+      float* o = p.sample_out + ((size_t)slice * p.nq_pad + q) * SAMPLE_R;
+#pragma unroll
+      for (int i = 0; i < SAMPLE_R; ++i) o[i] = top[i];
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// thr[q] = r-th largest of the sampled scores of query q (over all slices); -inf if fewer.
+// One CTA per query, values staged in shared memory, r rounds of block-wide arg-max.
+__global__ void __launch_bounds__(256)
+select_threshold_kernel(const float* __restrict__ sample, int nslices, int nq_pad, int nq, int r, float* thr) {
+  extern __shared__ float vals[];
+  __shared__ float wmax[8];
+  __shared__ int widx[8];
+  __shared__ float result;
+  const int q = blockIdx.x;
+  const int n = nslices * SAMPLE_R;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int s = i / SAMPLE_R, k = i % SAMPLE_R;
+    vals[i] = sample[((size_t)s * nq_pad + q) * SAMPLE_R + k];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int round = 0; round < r; ++round) {
+    float best = -INFINITY;
+    int bi = -1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float v = vals[i];
+      if (v > best) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi > bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { wmax[warp] = best; widx[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float b = wmax[0]; int idx = widx[0];
+      for (int w = 1; w < 8; ++w) if (wmax[w] > b || (wmax[w] == b && widx[w] > idx)) { b = wmax[w]; idx = widx[w]; }
+      result = b;
+      if (idx >= 0) vals[idx] = -INFINITY;   // remove it for the next round
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) thr[q] = result;
+}
+
+__global__ void fill_kernel(float* p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 [rows, pitch] row-major, box = [box_rows, 64 columns], 128-byte swizzle, OOB rows read as 0.
+static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, int pitch, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return TT_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return TT_ERR_CUDA;
+  }
+  return TT_OK;
+}
+
+ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
+  ScanPlan pl{};
+  pl.Dp = (int)tt_flat_pitch(D);
+  pl.num_kb = pl.Dp / BLOCK_K;
+  // A (queries) stays resident: M=128 while it leaves room for >= 3 B stages, else M=64.
+  const int budget = 227 * 1024 - 2048;   // barriers + alignment slack
+  pl.block_m = 128;
+  if (budget - pl.num_kb * 128 * 128 < 3 * B_STAGE_BYTES) pl.block_m = 64;
+  const int a_bytes = pl.num_kb * pl.block_m * 128;
+  pl.num_stages = (budget - a_bytes) / B_STAGE_BYTES;
+  if (pl.num_stages > MAX_STAGES) pl.num_stages = MAX_STAGES;
+  pl.supported = pl.num_stages >= 2;
+  pl.smem_bytes = (size_t)a_bytes + (size_t)pl.num_stages * B_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  pl.nqb = (nq + pl.block_m - 1) / pl.block_m;
+  pl.nq_pad = pl.nqb * pl.block_m;
+  pl.num_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
+
+  // candidate budget: target T candidates per query, capacity C
+  int T = 4 * K;
+  if (T < 512) T = 512;
+  pl.target = T;
+  int C = 4096;
+  while (C < 4 * T) C <<= 1;
+  if (C > FINALIZE_MAX_CAND) C = FINALIZE_MAX_CAND;
+  pl.use_threshold = N > (long long)C / 2;
+  if (!pl.use_threshold) { while (C < N) C <<= 1; }
+  pl.cand_cap = C;
+
+  const int sms = num_sms();
+  // main scan grid: nqb query blocks x nslices catalog slices
+  int ns = sms / pl.nqb;
+  if (ns < 1) ns = 1;
+  if (ns > pl.num_tiles) ns = pl.num_tiles;
+  pl.main_slices = ns;
+
+  // sample pass
+  pl.sample_stride = T / 16;
+  if (pl.sample_stride < 1) pl.sample_stride = 1;
+  pl.sample_slots = (pl.num_tiles + pl.sample_stride - 1) / pl.sample_stride;
+  int ss = sms / pl.nqb;
+  if (ss < 1) ss = 1;
+  if (ss > pl.sample_slots) ss = pl.sample_slots;
+  pl.sample_slices = ss;
+  // rows actually covered by the sampled tiles
+  long long ns_rows = 0;
+  {
+    const long long last_slot = pl.sample_slots - 1;
+    ns_rows = last_slot * BLOCK_N;
+    const long long last_row0 = last_slot * (long long)pl.sample_stride * BLOCK_N;
+    long long rem = N - last_row0;
+    if (rem > BLOCK_N) rem = BLOCK_N;
+    ns_rows += rem;
+  }
+  long long r = (long long)((double)T * (double)ns_rows / (double)N);
+  if (r < 1) r = 1;
+  if (r > SAMPLE_R) r = SAMPLE_R;
+  pl.sample_rank = (int)r;
+  return pl;
+}
+
+template <int BLOCK_M, bool SAMPLE>
+static int launch_scan_t(const CUtensorMap& tq, const CUtensorMap& tx, const ScanParams& sp, int grid, size_t smem,
+                         cudaStream_t st) {
+  TT_CHECK_CUDA(cudaFuncSetAttribute(flat_scan_kernel<BLOCK_M, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  flat_scan_kernel<BLOCK_M, SAMPLE><<<grid, SCAN_THREADS, smem, st>>>(tq, tx, sp);
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}
+
+int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq,
+                float* thr, unsigned int* cand_cnt, void* cand, float* sample_buf, cudaStream_t st) {
+  CUtensorMap tq, tx;
+  if (int e = make_tmap_bf16(&tq, qh, pl.nq_pad, pl.Dp, pl.block_m)) return e;
+  if (int e = make_tmap_bf16(&tx, Xh, N, pl.Dp, BLOCK_N)) return e;
+
+  ScanParams sp{};
+  sp.N = N; sp.nq = nq; sp.num_kb = pl.num_kb; sp.num_stages = pl.num_stages; sp.nqb = pl.nqb;
+  sp.thr = thr; sp.cand_cnt = cand_cnt; sp.cand = reinterpret_cast<uint2*>(cand); sp.cand_cap = pl.cand_cap;
+  sp.sample_out = sample_buf; sp.nq_pad = pl.nq_pad;
+
+  if (pl.use_threshold) {
+    sp.num_slots = pl.sample_slots; sp.tile_stride = pl.sample_stride;
+    const int grid = pl.sample_slices * pl.nqb;
+    int e = (pl.block_m == 128) ? launch_scan_t<128, true>(tq, tx, sp, grid, pl.smem_bytes, st)
+                                : launch_scan_t<64, true>(tq, tx, sp, grid, pl.smem_bytes, st);
+    if (e) return e;
+    const size_t sm = (size_t)pl.sample_slices * SAMPLE_R * sizeof(float);
+    select_threshold_kernel<<<nq, 256, sm, st>>>(sample_buf, pl.sample_slices, pl.nq_pad, nq, pl.sample_rank, thr);
+    TT_CHECK_LAUNCH();
+  } else {
+    fill_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thr, nq, -INFINITY);
+    TT_CHECK_LAUNCH();
+  }
+  sp.num_slots = pl.num_tiles; sp.tile_stride = 1;
+  const int grid = pl.main_slices * pl.nqb;
+  return (pl.block_m == 128) ? launch_scan_t<128, false>(tq, tx, sp, grid, pl.smem_bytes, st)
+                             : launch_scan_t<64, false>(tq, tx, sp, grid, pl.smem_bytes, st);
+}
+
+}  // namespace tt

@@ -1,0 +1,386 @@
+// Selection side of the exact inner-product search:
+//   finalize : fp32 rescoring of the candidate lists the tensor-core scan produced, exact sort by
+//              (score desc, row asc), and the per-query exactness certificate
+//   merge    : G sorted per-shard top-K lists -> one top-K (multi-GPU path)
+//   exact    : always-exact fp32 path (CUDA-core scoring, 64-bit radix select), used for queries
+//              the certificate rejects and as an on-device cross-check
+// Semantics follow faiss.IndexFlatIP.search as used at src/inference/vector_db.py:160,197:
+// fp32 inner products, k largest, sorted descending, int64 labels.
+#include "tt_common.cuh"
+#include "flat_internal.cuh"
+
+namespace tt {
+
+// In-place bitonic sort of P (power of two) 64-bit keys in shared memory, descending.
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* key, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = key[i], b = key[ixj];
+          const bool up = (i & k) == 0;          // "up" blocks are sorted descending
+          if (up ? (a < b) : (a > b)) { key[i] = b; key[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int n) {
+  int p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+// fp32 dot of a shared-memory query with a global row, warp-cooperative.
+__device__ __forceinline__ float warp_dot(const float* __restrict__ qs, const float* __restrict__ row, int D,
+                                          int lane, bool vec) {
+  float a = 0.f;
+  if (vec) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const float4* q4 = reinterpret_cast<const float4*>(qs);
+    for (int c = lane; c < (D >> 2); c += 32) {
+      const float4 x = __ldg(r4 + c);
+      const float4 y = q4[c];
+      a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
+    }
+  } else {
+    for (int d = lane; d < D; d += 32) a = fmaf(__ldg(row + d), qs[d], a);
+  }
+  return warp_sum(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: one CTA per query
+__global__ void __launch_bounds__(256)
+flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn, long long N, int D, int K,
+                     long long id_offset, const float* __restrict__ thr, const float* __restrict__ eps,
+                     const unsigned int* __restrict__ cand_cnt, const uint2* __restrict__ cand, int cand_cap,
+                     float* __restrict__ scores, long long* __restrict__ ids, int* __restrict__ flags,
+                     int* __restrict__ n_uncertified) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(fsm);
+  const int q = blockIdx.x;
+  const unsigned int n_raw = cand_cnt[q];
+  const bool overflow = n_raw > (unsigned int)cand_cap;
+  const int n = overflow ? cand_cap : (int)n_raw;
+  const int P = next_pow2(n < 2 ? 2 : n);   // >= 2 keeps qs 16-byte aligned
+  float* qs = reinterpret_cast<float*>(key + P);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) qs[d] = qn[(long long)q * D + d];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(Xn) & 15) == 0);
+  const uint2* mine = cand + (size_t)q * cand_cap;
+  const float my_eps = eps[q];
+  int bad = 0;   // self-check: a candidate's tensor-core score must match its fp32 rescoring within eps
+  for (int i = warp; i < n; i += nwarps) {
+    const uint2 c = mine[i];
+    const uint32_t row = c.y;
+    if ((long long)row >= N) {            // cannot happen unless the scan is broken
+      if (lane == 0) { key[i] = 0ull; bad = 1; }
+      continue;
+    }
+    const float s = warp_dot(qs, Xn + (long long)row * D, D, lane, vec);
+    if (lane == 0) {
+      key[i] = make_key(s, row);
+      if (!(fabsf(__uint_as_float(c.x) - s) <= my_eps)) bad = 1;
+    }
+  }
+  for (int i = n + threadIdx.x; i < P; i += blockDim.x) key[i] = 0ull;
+  const int any_bad = __syncthreads_or(bad);
+  bitonic_sort_desc(key, P);
+
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    if (i < n) {
+      scores[(long long)q * K + i] = key_score(key[i]);
+      ids[(long long)q * K + i] = (long long)key_row(key[i]) + id_offset;
+    } else {
+      scores[(long long)q * K + i] = -INFINITY;
+      ids[(long long)q * K + i] = -1;
+    }
+  }
+  if (threadIdx.x == 0) {
+    // Certificate.  Rows outside the candidate list have a bf16 tensor-core score < thr, hence an
+    // fp32 score < thr + eps.  If the K-th best rescored candidate reaches thr + eps, none of them
+    // can enter (or tie into) the top-K.
+    const float t = thr[q];
+    bool ok = !overflow && n >= K && !any_bad;
+    if (ok && !(t == -INFINITY)) ok = key_score(key[K - 1]) >= t + my_eps;
+    flags[q] = ok ? 1 : 0;
+    if (!ok) atomicAdd(n_uncertified, 1);
+  }
+}
+
+int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long long N, int D, int nq, int K,
+                    long long id_offset, const float* thr, const float* eps, const unsigned int* cand_cnt,
+                    const void* cand, float* scores, long long* ids, int* flags, int* n_uncertified,
+                    cudaStream_t st) {
+  const size_t smem = (size_t)pl.cand_cap * 8 + (size_t)D * 4 + 16;
+  TT_CHECK_CUDA(cudaFuncSetAttribute(flat_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  flat_finalize_kernel<<<nq, 256, smem, st>>>(qn, Xn, N, D, K, id_offset, thr, eps, cand_cnt,
+                                              reinterpret_cast<const uint2*>(cand), pl.cand_cap, scores, ids, flags,
+                                              n_uncertified);
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// merge: one CTA per query, G*K <= 16384 keys
+__global__ void __launch_bounds__(128)
+topk_merge_kernel(const float* __restrict__ sg, const long long* __restrict__ ig, int G, int nq, int K,
+                  float* __restrict__ scores, long long* __restrict__ ids) {
+  extern __shared__ __align__(16) unsigned char msm[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(msm);
+  const int q = blockIdx.x;
+  const int n = G * K;
+  const int P = next_pow2(n);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    unsigned long long kk = 0ull;
+    if (i < n) {
+      const int g = i / K, j = i % K;
+      const long long id = ig[((long long)g * nq + q) * K + j];
+      const float s = sg[((long long)g * nq + q) * K + j];
+      if (id >= 0) kk = make_key(s, (uint32_t)id);
+    }
+    key[i] = kk;
+  }
+  __syncthreads();
+  bitonic_sort_desc(key, P);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const unsigned long long kk = key[i];
+    scores[(long long)q * K + i] = (kk == 0ull) ? -INFINITY : key_score(kk);
+    ids[(long long)q * K + i] = (kk == 0ull) ? -1 : (long long)key_row(kk);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact path
+constexpr int EX_QB = 8;   // queries scored per pass over the fp32 table
+
+struct SelState {
+  unsigned long long prefix;   // bits of the K-th key decided so far
+  int kremain;                 // rank still to resolve inside the current prefix bucket
+  unsigned int count;          // collect cursor
+};
+
+// scores_ws[slot, r] = <q_slot / (||q_slot|| + 1e-8), Xn[r]>
+__global__ void __launch_bounds__(256)
+exact_scores_kernel(const float* __restrict__ q, const int* __restrict__ qsel, int slot0, int nslot,
+                    const float* __restrict__ Xn, long long N, int D, float* __restrict__ scores_ws) {
+  extern __shared__ __align__(16) float qs[];   // [nslot][D]
+  __shared__ float inv[EX_QB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int s = warp; s < nslot; s += nwarps) {
+    const int qi = qsel ? qsel[slot0 + s] : (slot0 + s);
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float v = q[(long long)qi * D + d]; ss += v * v; }
+    ss = warp_sum(ss);
+    if (lane == 0) inv[s] = sqrtf(ss) + 1e-8f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nslot * D; i += blockDim.x) {
+    const int s = i / D, d = i % D;
+    const int qi = qsel ? qsel[slot0 + s] : (slot0 + s);
+    qs[i] = q[(long long)qi * D + d] / inv[s];
+  }
+  __syncthreads();
+  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(Xn) & 15) == 0);
+  const long long gw = (long long)blockIdx.x * nwarps + warp;
+  const long long tw = (long long)gridDim.x * nwarps;
+  for (long long r = gw; r < N; r += tw) {
+    float acc[EX_QB];
+#pragma unroll
+    for (int s = 0; s < EX_QB; ++s) acc[s] = 0.f;
+    const float* row = Xn + r * D;
+    if (vec) {
+      const float4* r4 = reinterpret_cast<const float4*>(row);
+      for (int c = lane; c < (D >> 2); c += 32) {
+        const float4 x = ldg_stream(r4 + c);
+#pragma unroll
+        for (int s = 0; s < EX_QB; ++s) {
+          if (s < nslot) {
+            const float4 y = reinterpret_cast<const float4*>(qs + s * D)[c];
+            acc[s] = fmaf(x.x, y.x, acc[s]); acc[s] = fmaf(x.y, y.y, acc[s]);
+            acc[s] = fmaf(x.z, y.z, acc[s]); acc[s] = fmaf(x.w, y.w, acc[s]);
+          }
+        }
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) {
+        const float x = __ldg(row + d);
+#pragma unroll
+        for (int s = 0; s < EX_QB; ++s) if (s < nslot) acc[s] = fmaf(x, qs[s * D + d], acc[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < EX_QB; ++s) {
+      if (s < nslot) {
+        const float v = warp_sum(acc[s]);
+        if (lane == 0) scores_ws[(long long)s * N + r] = v;
+      }
+    }
+  }
+}
+
+__global__ void exact_init_kernel(SelState* st, unsigned int* hist, int nslot, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nslot) { st[i].prefix = 0ull; st[i].kremain = K; st[i].count = 0u; }
+  if (i < nslot * 256) hist[i] = 0u;
+}
+
+// histogram of the digit at `shift` over keys whose higher bits equal the prefix
+__global__ void __launch_bounds__(256)
+exact_hist_kernel(const float* __restrict__ scores_ws, long long N, const SelState* __restrict__ st,
+                  unsigned int* __restrict__ hist, int shift) {
+  __shared__ unsigned int h[256];
+  const int s = blockIdx.y;
+  h[threadIdx.x] = 0u;
+  __syncthreads();
+  const unsigned long long prefix = st[s].prefix;
+  const float* sc = scores_ws + (long long)s * N;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long k = make_key(sc[r], (uint32_t)r);
+    const bool match = (shift == 56) ? true : ((k >> (shift + 8)) == (prefix >> (shift + 8)));
+    if (match) atomicAdd(&h[(unsigned int)(k >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) atomicAdd(&hist[s * 256 + threadIdx.x], h[threadIdx.x]);
+}
+
+// choose the digit containing the kremain-th largest key, then clear the histogram
+__global__ void exact_pick_kernel(SelState* st, unsigned int* hist, int shift) {
+  const int s = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int krem = st[s].kremain;
+    int d = 255;
+    unsigned int above = 0;
+    for (; d > 0; --d) {
+      const unsigned int c = hist[s * 256 + d];
+      if (above + c >= (unsigned int)krem) break;
+      above += c;
+    }
+    st[s].prefix |= ((unsigned long long)d) << shift;
+    st[s].kremain = krem - (int)above;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[s * 256 + i] = 0u;
+}
+
+__global__ void __launch_bounds__(256)
+exact_collect_kernel(const float* __restrict__ scores_ws, long long N, SelState* st, unsigned long long* keys_out, int K) {
+  const int s = blockIdx.y;
+  const unsigned long long kth = st[s].prefix;
+  const float* sc = scores_ws + (long long)s * N;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long k = make_key(sc[r], (uint32_t)r);
+    if (k >= kth) {
+      const unsigned int pos = atomicAdd(&st[s].count, 1u);
+      if (pos < (unsigned int)K) keys_out[(long long)s * K + pos] = k;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+exact_sort_kernel(const unsigned long long* __restrict__ keys_in, const int* __restrict__ qsel, int slot0, int K,
+                  long long id_offset, float* __restrict__ scores, long long* __restrict__ ids) {
+  extern __shared__ __align__(16) unsigned char ssm[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(ssm);
+  const int s = blockIdx.x;
+  const int qi = qsel ? qsel[slot0 + s] : (slot0 + s);
+  const int P = next_pow2(K);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) key[i] = (i < K) ? keys_in[(long long)s * K + i] : 0ull;
+  __syncthreads();
+  bitonic_sort_desc(key, P);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    scores[(long long)qi * K + i] = key_score(key[i]);
+    ids[(long long)qi * K + i] = (long long)key_row(key[i]) + id_offset;
+  }
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" __attribute__((visibility("default"))) int tt_topk_merge(const float* scores_g, const int64_t* ids_g, int G, int nq, int K,
+                             float* scores, int64_t* ids, void* stream) {
+  TT_CHECK_ARG(scores_g && ids_g && scores && ids, "null pointer");
+  TT_CHECK_ARG(G >= 1 && nq >= 0 && K >= 1, "need G >= 1, nq >= 0, K >= 1");
+  TT_CHECK_ARG((long long)G * K <= FINALIZE_MAX_CAND, "G*K exceeds 16384");
+  if (nq == 0) return TT_OK;
+  int P = 1;
+  while (P < G * K) P <<= 1;
+  const size_t smem = (size_t)P * 8;
+  TT_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_merge_kernel<<<nq, 128, smem, (cudaStream_t)stream>>>(scores_g, reinterpret_cast<const long long*>(ids_g), G,
+                                                            nq, K, scores, reinterpret_cast<long long*>(ids));
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}
+
+static size_t exact_ws_layout(int64_t N, int K, size_t* off_state, size_t* off_hist, size_t* off_keys) {
+  size_t o = 0;
+  o += align_up((size_t)EX_QB * (size_t)N * sizeof(float), 256);
+  *off_state = o; o += align_up(EX_QB * sizeof(SelState), 256);
+  *off_hist = o;  o += align_up(EX_QB * 256 * sizeof(unsigned int), 256);
+  *off_keys = o;  o += align_up((size_t)EX_QB * K * sizeof(unsigned long long), 256);
+  return o;
+}
+
+extern "C" __attribute__((visibility("default"))) size_t tt_flat_search_exact_workspace_bytes(int64_t N, int D, int nsel, int K) {
+  (void)D; (void)nsel;
+  size_t a, b, c;
+  return exact_ws_layout(N, K, &a, &b, &c);
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_flat_search_exact(const float* q, int nq, const int32_t* qsel, int nsel,
+                                    const float* Xn, int64_t N, int D, int K, int64_t id_offset,
+                                    float* scores, int64_t* ids, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  TT_CHECK_ARG(q && Xn && scores && ids && workspace, "null pointer");
+  TT_CHECK_ARG(N >= 1 && N < (1LL << 32) && D >= 1, "need 1 <= N < 2^32, D >= 1");
+  TT_CHECK_ARG(K >= 1 && K <= N && K <= TT_FLAT_MAX_K, "need 1 <= K <= min(N, TT_FLAT_MAX_K)");
+  TT_CHECK_ARG(nq >= 0 && nsel >= 0 && (qsel != nullptr || nsel == nq), "qsel == NULL requires nsel == nq");
+  TT_CHECK_ARG((size_t)EX_QB * D * sizeof(float) <= 160 * 1024, "D too large");
+  if (nsel == 0) return TT_OK;
+  size_t o_state, o_hist, o_keys;
+  const size_t need = exact_ws_layout(N, K, &o_state, &o_hist, &o_keys);
+  if (workspace_bytes < need) { set_error("tt_flat_search_exact: workspace too small"); return TT_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  float* scores_ws = reinterpret_cast<float*>(ws);
+  SelState* state = reinterpret_cast<SelState*>(ws + o_state);
+  unsigned int* hist = reinterpret_cast<unsigned int*>(ws + o_hist);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + o_keys);
+
+  const int sms = num_sms();
+  const size_t smem_q = (size_t)EX_QB * D * sizeof(float);
+  TT_CHECK_CUDA(cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+  int P = 1;
+  while (P < K) P <<= 1;
+  long long gs = (N + 255) / 256;
+  if (gs > (long long)sms * 8) gs = (long long)sms * 8;
+  for (int slot0 = 0; slot0 < nsel; slot0 += EX_QB) {
+    const int nslot = (nsel - slot0 < EX_QB) ? (nsel - slot0) : EX_QB;
+    long long gw = (N + 7) / 8;
+    if (gw > (long long)sms * 4) gw = (long long)sms * 4;
+    exact_scores_kernel<<<(unsigned)gw, 256, smem_q, st>>>(q, qsel, slot0, nslot, Xn, N, D, scores_ws);
+    TT_CHECK_LAUNCH();
+    exact_init_kernel<<<(nslot * 256 + 255) / 256, 256, 0, st>>>(state, hist, nslot, K);
+    TT_CHECK_LAUNCH();
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      exact_hist_kernel<<<dim3((unsigned)gs, nslot), 256, 0, st>>>(scores_ws, N, state, hist, shift);
+      TT_CHECK_LAUNCH();
+      exact_pick_kernel<<<nslot, 256, 0, st>>>(state, hist, shift);
+      TT_CHECK_LAUNCH();
+    }
+    exact_collect_kernel<<<dim3((unsigned)gs, nslot), 256, 0, st>>>(scores_ws, N, state, keys, K);
+    TT_CHECK_LAUNCH();
+    exact_sort_kernel<<<nslot, 256, (size_t)P * 8, st>>>(keys, qsel, slot0, K, id_offset, scores,
+                                                         reinterpret_cast<long long*>(ids));
+    TT_CHECK_LAUNCH();
+  }
+  return TT_OK;
+}

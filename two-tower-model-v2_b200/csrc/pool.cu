@@ -1,0 +1,301 @@
+// Buyer-tower pooling kernels (reference: src/models/buyer_tower.py:43-101).
+//
+// One fused kernel does, per buyer: per-event coefficients (normalised event weights, or the
+// softmax of logit*weight), the coefficient-weighted sum of S item-embedding rows, and the
+// final L2 normalisation.  Rows are read exactly once with coalesced 128-bit loads (a warp
+// covers 512 contiguous bytes per load instruction); reductions are warp shuffles.  The
+// kernel is HBM-bound: algorithmic bytes = B*S*D*4 + B*S*4 (+ B*S*8 idx, + B*S*4 logits) + B*D*4.
+#include "tt_common.cuh"
+
+namespace tt {
+
+struct PoolParams {
+  const float* x;        // dense [B,S,D] or table [N,D]
+  const int64_t* idx;    // gather only: [B,S]
+  const float* w;        // [B,S]
+  const float* logits;   // attention: dense [B,S]; gather: per-table-row [N]
+  float* out;            // [B,D]
+  long long N;           // table rows (gather)
+  float zero_row_logit;  // attention+gather: logit of an all-zero row
+  int B, S, D;
+};
+
+template <bool GATHER, bool ATTN>
+__device__ __forceinline__ float load_c(const PoolParams& p, int b, int s, long long& row) {
+  // returns w (weighted) or logit*w (attention); sets row index (gather) / -1 invalid
+  const long long bs = (long long)b * p.S + s;
+  const float w = __ldg(p.w + bs);
+  if (GATHER) {
+    const long long r = __ldg((const long long*)p.idx + bs);
+    row = (r >= 0 && r < p.N) ? r : -1;
+  } else {
+    row = bs;
+  }
+  if (ATTN) {
+    float lg;
+    if (GATHER) lg = (row >= 0) ? __ldg(p.logits + row) : p.zero_row_logit;
+    else lg = __ldg(p.logits + bs);
+    return lg * w;   // buyer_tower.py:89  combined_scores = attention_scores * weights
+  }
+  return w;
+}
+
+// NV   : float4 per lane per row (ceil(D/128))
+// WPB  : warps cooperating on one buyer (1 or WARPS)
+// U    : rows in flight per warp
+template <int NV, int WARPS, int WPB, int U, bool GATHER, bool ATTN>
+__global__ void __launch_bounds__(WARPS * 32, (WPB == 1) ? (NV <= 3 ? 7 : (NV <= 4 ? 5 : 3)) : 1)
+pool_vec_kernel(const PoolParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int buyers_per_cta = WARPS / WPB;
+  const int b = blockIdx.x * buyers_per_cta + (WPB == 1 ? warp : 0);
+  const int sub = (WPB == 1) ? 0 : warp;   // which slice of rows this warp takes
+  const bool active = b < p.B;             // warp-uniform
+
+  __shared__ float4 red[(WPB > 1) ? WARPS * NV * 32 : 1];
+
+  float4 acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  if (active) {
+    const int S = p.S, D = p.D;
+    // ---- pass 1: normaliser of the coefficients (tiny; w/logits stay in L1) -------------
+    float m = -INFINITY, tot = 0.f;
+    if (ATTN) {
+      for (int s = lane; s < S; s += 32) { long long r; m = fmaxf(m, load_c<GATHER, ATTN>(p, b, s, r)); }
+      m = warp_max(m);
+      for (int s = lane; s < S; s += 32) { long long r; tot += expf(load_c<GATHER, ATTN>(p, b, s, r) - m); }
+      tot = warp_sum(tot);
+    } else {
+      for (int s = lane; s < S; s += 32) tot += __ldg(p.w + (long long)b * S + s);
+      tot = warp_sum(tot) + 1e-8f;   // buyer_tower.py:59
+    }
+
+    // ---- pass 2: weighted row sum ---------------------------------------------------------
+    const int nvalid4 = D >> 2;   // float4 per row
+    for (int s0 = 0; s0 < S; s0 += 32) {
+      const int s = s0 + lane;
+      float coef = 0.f;
+      long long row = -1;
+      if (s < S) {
+        const float c = load_c<GATHER, ATTN>(p, b, s, row);
+        coef = ATTN ? (expf(c - m) / tot)   // softmax, buyer_tower.py:92
+                    : (c / tot);            // weights / weights_sum, buyer_tower.py:60
+      }
+      const int nrow = min(32, S - s0);
+      // this warp handles rows j = sub, sub+WPB, ... of the chunk, U at a time
+      for (int j0 = sub; j0 < nrow; j0 += WPB * U) {
+        float4 buf[U][NV];
+        float cf[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u * WPB;
+          const int jj = (j < nrow) ? j : 0;
+          const float cj = __shfl_sync(0xffffffffu, coef, jj);
+          const long long rj = __shfl_sync(0xffffffffu, row, jj);
+          const bool ok = (j < nrow) && (rj >= 0);
+          cf[u] = ok ? cj : 0.f;
+          const float4* rp = reinterpret_cast<const float4*>(p.x + (ok ? rj : 0) * (long long)D);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int c4 = v * 32 + lane;
+            if (ok && c4 < nvalid4) buf[u][v] = ldg_stream(rp + c4);
+            else buf[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            acc[v].x = fmaf(buf[u][v].x, cf[u], acc[v].x);
+            acc[v].y = fmaf(buf[u][v].y, cf[u], acc[v].y);
+            acc[v].z = fmaf(buf[u][v].z, cf[u], acc[v].z);
+            acc[v].w = fmaf(buf[u][v].w, cf[u], acc[v].w);
+          }
+        }
+      }
+    }
+  }
+
+  if (WPB > 1) {
+    // cross-warp reduction of the partial sums (small-B path: one buyer per CTA)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) red[(warp * NV + v) * 32 + lane] = acc[v];
+    __syncthreads();
+    if (warp != 0) return;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float4 t = red[v * 32 + lane];
+      for (int w2 = 1; w2 < WARPS; ++w2) {
+        const float4 o = red[(w2 * NV + v) * 32 + lane];
+        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+      }
+      acc[v] = t;
+    }
+  }
+  if (!active) return;
+
+  // ---- L2 normalisation: F.normalize(p=2, dim=1, eps=1e-12)  buyer_tower.py:66/:99 ------
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+    ss += acc[v].x * acc[v].x + acc[v].y * acc[v].y + acc[v].z * acc[v].z + acc[v].w * acc[v].w;
+  ss = warp_sum(ss);
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  float4* op = reinterpret_cast<float4*>(p.out + (long long)b * p.D);
+  const int nvalid4 = p.D >> 2;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c4 = v * 32 + lane;
+    if (c4 < nvalid4)
+      op[c4] = make_float4(acc[v].x / denom, acc[v].y / denom, acc[v].z / denom, acc[v].w / denom);
+  }
+}
+
+// Generic fallback for shapes the vector kernel does not take (D % 4 != 0, D > 1024 or an
+// unaligned base pointer): one CTA per buyer, threads stride over d.  Still a CUDA kernel.
+template <bool GATHER, bool ATTN>
+__global__ void __launch_bounds__(256)
+pool_generic_kernel(const PoolParams p) {
+  extern __shared__ float sm[];      // coef[S] + rowoff as 2 floats each -> keep separate arrays
+  float* coef = sm;
+  long long* rows = reinterpret_cast<long long*>(sm + ((p.S + 1) & ~1));
+  __shared__ float red[32];
+  __shared__ float bc[2];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = p.S, D = p.D;
+
+  float m = -INFINITY;
+  for (int s = tid; s < S; s += blockDim.x) {
+    long long r; const float c = load_c<GATHER, ATTN>(p, b, s, r);
+    coef[s] = c; rows[s] = r; m = fmaxf(m, c);
+  }
+  if (ATTN) {
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (tid == 0) { float t = red[0]; for (int i = 1; i < (int)(blockDim.x >> 5); ++i) t = fmaxf(t, red[i]); bc[0] = t; }
+    __syncthreads();
+    m = bc[0];
+  }
+  __syncthreads();
+  float tot = 0.f;
+  for (int s = tid; s < S; s += blockDim.x) tot += ATTN ? expf(coef[s] - m) : coef[s];
+  tot = warp_sum(tot);
+  if (lane == 0) red[warp] = tot;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i]; bc[1] = ATTN ? t : t + 1e-8f; }
+  __syncthreads();
+  tot = bc[1];
+  for (int s = tid; s < S; s += blockDim.x) coef[s] = ATTN ? expf(coef[s] - m) / tot : coef[s] / tot;
+  __syncthreads();
+
+  float ss = 0.f;
+  for (int d = tid; d < D; d += blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const long long r = rows[s];
+      if (r >= 0) a = fmaf(__ldg(p.x + r * (long long)D + d), coef[s], a);
+    }
+    p.out[(long long)b * D + d] = a;   // un-normalised; scaled below
+    ss += a * a;
+  }
+  ss = warp_sum(ss);
+  __syncthreads();
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i]; bc[0] = fmaxf(sqrtf(t), 1e-12f); }
+  __syncthreads();
+  const float denom = bc[0];
+  for (int d = tid; d < D; d += blockDim.x) p.out[(long long)b * D + d] /= denom;
+}
+
+template <int NV, bool GATHER, bool ATTN>
+static int launch_vec(const PoolParams& p, cudaStream_t st) {
+  // Many buyers: one warp per buyer, 4 warps per CTA, 7 CTAs per SM => 28 resident warps/SM,
+  // i.e. 4144 buyers in a single wave on 148 SMs.  Few buyers: 8 warps share one buyer.
+  if (p.B >= 2 * num_sms()) {
+    constexpr int WARPS = 4;
+    const int grid = (p.B + WARPS - 1) / WARPS;
+    pool_vec_kernel<NV, WARPS, 1, 2, GATHER, ATTN><<<grid, WARPS * 32, 0, st>>>(p);
+  } else {
+    constexpr int WARPS = 8;
+    pool_vec_kernel<NV, WARPS, WARPS, 4, GATHER, ATTN><<<p.B, WARPS * 32, 0, st>>>(p);
+  }
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}
+
+template <bool GATHER, bool ATTN>
+static int launch_pool(const PoolParams& p, cudaStream_t st) {
+  const bool vec_ok = (p.D % 4 == 0) && (p.D <= 1024) &&
+                      ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+  if (vec_ok) {
+    const int nv = (p.D + 127) / 128;
+    switch (nv) {
+      case 1: return launch_vec<1, GATHER, ATTN>(p, st);
+      case 2: return launch_vec<2, GATHER, ATTN>(p, st);
+      case 3: return launch_vec<3, GATHER, ATTN>(p, st);
+      case 4: return launch_vec<4, GATHER, ATTN>(p, st);
+      case 5: case 6: return launch_vec<6, GATHER, ATTN>(p, st);
+      default: return launch_vec<8, GATHER, ATTN>(p, st);
+    }
+  }
+  const size_t smem = (size_t)((p.S + 1) & ~1) * sizeof(float) + (size_t)p.S * sizeof(long long);
+  if (smem > 200 * 1024) { set_error("pool: S too large for the generic kernel"); return TT_ERR_UNSUPPORTED; }
+  if (smem > 48 * 1024)
+    TT_CHECK_CUDA(cudaFuncSetAttribute(pool_generic_kernel<GATHER, ATTN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pool_generic_kernel<GATHER, ATTN><<<p.B, 256, smem, st>>>(p);
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}
+
+static int check_common(const void* x, const void* w, const void* out, int B, int S, int D) {
+  TT_CHECK_ARG(x && w && out, "null pointer");
+  TT_CHECK_ARG(B >= 0 && S >= 1 && D >= 1, "need B >= 0, S >= 1, D >= 1");
+  return TT_OK;
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" __attribute__((visibility("default"))) int tt_pool_weighted(const float* x, const float* w, float* out, int B, int S, int D, void* stream) {
+  if (int e = check_common(x, w, out, B, S, D)) return e;
+  if (B == 0) return TT_OK;
+  PoolParams p{}; p.x = x; p.w = w; p.out = out; p.B = B; p.S = S; p.D = D;
+  return launch_pool<false, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_pool_weighted_gather(const float* table, int64_t N, const int64_t* idx, const float* w,
+                                       float* out, int B, int S, int D, void* stream) {
+  if (int e = check_common(table, w, out, B, S, D)) return e;
+  TT_CHECK_ARG(idx != nullptr && N >= 1, "null idx or empty table");
+  if (B == 0) return TT_OK;
+  PoolParams p{}; p.x = table; p.idx = idx; p.w = w; p.out = out; p.N = N; p.B = B; p.S = S; p.D = D;
+  return launch_pool<true, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_pool_attention(const float* x, const float* logits, const float* w, float* out,
+                                 int B, int S, int D, void* stream) {
+  if (int e = check_common(x, w, out, B, S, D)) return e;
+  TT_CHECK_ARG(logits != nullptr, "null logits");
+  if (B == 0) return TT_OK;
+  PoolParams p{}; p.x = x; p.w = w; p.logits = logits; p.out = out; p.B = B; p.S = S; p.D = D;
+  return launch_pool<false, true>(p, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_pool_attention_gather(const float* table, int64_t N, const float* row_logits,
+                                        float zero_row_logit, const int64_t* idx, const float* w,
+                                        float* out, int B, int S, int D, void* stream) {
+  if (int e = check_common(table, w, out, B, S, D)) return e;
+  TT_CHECK_ARG(idx != nullptr && row_logits != nullptr && N >= 1, "null idx/logits or empty table");
+  if (B == 0) return TT_OK;
+  PoolParams p{}; p.x = table; p.idx = idx; p.w = w; p.logits = row_logits; p.zero_row_logit = zero_row_logit;
+  p.out = out; p.N = N; p.B = B; p.S = S; p.D = D;
+  return launch_pool<true, true>(p, (cudaStream_t)stream);
+}

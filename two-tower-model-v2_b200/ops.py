@@ -1,0 +1,103 @@
+"""PyTorch ops over the C-ABI: `torch.ops.tt.*`, CUDA only.
+
+Each op allocates its outputs with torch (device memory + current stream are torch's job: plumbing)
+and hands raw pointers to libtt_b200.so.  There is no CPU or Meta implementation on purpose.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+from . import _native
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"tt_b200: `{name}` must be a CUDA tensor (no CPU fallback); got {t.device}")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+@torch.library.custom_op("tt::pool_weighted", mutates_args=(), device_types="cuda")
+def pool_weighted(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """buyer_tower.py:43-68 — x [B,S,D], w [B,S] -> [B,D]."""
+    B, S, D = x.shape
+    out = torch.empty((B, D), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _native.check(_native.load().tt_pool_weighted(x.data_ptr(), w.data_ptr(), out.data_ptr(), B, S, D, _stream()),
+                      "tt_pool_weighted")
+    return out
+
+
+@torch.library.custom_op("tt::pool_weighted_gather", mutates_args=(), device_types="cuda")
+def pool_weighted_gather(table: torch.Tensor, idx: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """Same as pool_weighted with rows x[b,s] = table[idx[b,s]] (idx out of range = zero row)."""
+    N, D = table.shape
+    B, S = idx.shape
+    out = torch.empty((B, D), device=table.device, dtype=torch.float32)
+    with torch.cuda.device(table.device):
+        _native.check(_native.load().tt_pool_weighted_gather(table.data_ptr(), N, idx.data_ptr(), w.data_ptr(),
+                                                             out.data_ptr(), B, S, D, _stream()),
+                      "tt_pool_weighted_gather")
+    return out
+
+
+@torch.library.custom_op("tt::attention_logits", mutates_args=(), device_types="cuda")
+def attention_logits(x: torch.Tensor, W1: torch.Tensor, b1: torch.Tensor, W2: torch.Tensor,
+                     b2: torch.Tensor) -> torch.Tensor:
+    """buyer_tower.py:85-86 — x [R,D] -> logits [R] = W2.relu(W1 x + b1) + b2 (fp32)."""
+    R, D = x.shape
+    H = W1.shape[0]
+    out = torch.empty((R,), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _native.check(_native.load().tt_attention_logits(x.data_ptr(), R, D, W1.data_ptr(), b1.data_ptr(),
+                                                         W2.data_ptr(), b2.data_ptr(), H, out.data_ptr(), _stream()),
+                      "tt_attention_logits")
+    return out
+
+
+@torch.library.custom_op("tt::pool_attention", mutates_args=(), device_types="cuda")
+def pool_attention(x: torch.Tensor, logits: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """buyer_tower.py:89-99 — softmax_s(logits*w)-weighted sum + L2 normalise."""
+    B, S, D = x.shape
+    out = torch.empty((B, D), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _native.check(_native.load().tt_pool_attention(x.data_ptr(), logits.data_ptr(), w.data_ptr(), out.data_ptr(),
+                                                       B, S, D, _stream()), "tt_pool_attention")
+    return out
+
+
+@torch.library.custom_op("tt::pool_attention_gather", mutates_args=(), device_types="cuda")
+def pool_attention_gather(table: torch.Tensor, row_logits: torch.Tensor, zero_row_logit: float,
+                          idx: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    N, D = table.shape
+    B, S = idx.shape
+    out = torch.empty((B, D), device=table.device, dtype=torch.float32)
+    with torch.cuda.device(table.device):
+        _native.check(_native.load().tt_pool_attention_gather(table.data_ptr(), N, row_logits.data_ptr(),
+                                                              float(zero_row_logit), idx.data_ptr(), w.data_ptr(),
+                                                              out.data_ptr(), B, S, D, _stream()),
+                      "tt_pool_attention_gather")
+    return out
+
+
+@torch.library.custom_op("tt::topk_merge", mutates_args=(), device_types="cuda")
+def topk_merge(scores_g: torch.Tensor, ids_g: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[G,nq,K] per-shard sorted lists -> [nq,K] (score desc, id asc)."""
+    G, nq, K = scores_g.shape
+    scores = torch.empty((nq, K), device=scores_g.device, dtype=torch.float32)
+    ids = torch.empty((nq, K), device=scores_g.device, dtype=torch.int64)
+    with torch.cuda.device(scores_g.device):
+        _native.check(_native.load().tt_topk_merge(scores_g.data_ptr(), ids_g.data_ptr(), G, nq, K,
+                                                   scores.data_ptr(), ids.data_ptr(), _stream()), "tt_topk_merge")
+    return scores, ids
+
+
+__all__ = ["pool_weighted", "pool_weighted_gather", "attention_logits", "pool_attention",
+           "pool_attention_gather", "topk_merge", "_f32c", "_stream"]

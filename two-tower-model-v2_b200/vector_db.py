@@ -1,0 +1,353 @@
+"""Vector database: drop-in for the reference `src/inference/vector_db.py:10-231`.
+
+`VectorDatabase` keeps the reference's constructor, attributes (`embedding_dim`, `index`,
+`product_ids`, `id_to_index`, `index_to_id`), methods, argument meaning, return types and
+exceptions.  `faiss.IndexFlatIP` is replaced by `FlatIPIndex`, a device-resident exact
+inner-product index searched by hand-written sm_100a kernels through the C-ABI
+(tt_flat_build / tt_flat_search / tt_flat_search_exact).  No faiss, no CPU search path.
+
+Beyond the reference surface: `search_batch` returns (scores, ids) arrays
+without building Python tuples, and load/save read and write the FAISS flat-index file layout
+(`IxFI`) so artefacts of `scripts/build_index.py` interoperate.
+"""
+from __future__ import annotations
+
+import json
+import struct
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native, ops
+
+# ---------------------------------------------------------------------------------------------
+# FAISS flat-index file layout [faiss-upstream, recalled; not verifiable here: faiss is absent]
+#   u32 fourcc "IxFI" | i32 d | i64 ntotal | i64 dummy(1<<20) | i64 dummy(1<<20) | u8 is_trained |
+#   i32 metric_type (0 = inner product) | u64 n_floats | f32[n_floats] row-major rows
+_FOURCC_IXFI = struct.unpack("<I", b"IxFI")[0]
+_HDR = struct.Struct("<IiqqqBiQ")   # 45 bytes, little endian, unpadded
+
+
+def write_flat_ip_file(path: str, rows: np.ndarray) -> None:
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    n, d = rows.shape
+    with open(path, "wb") as f:
+        f.write(_HDR.pack(_FOURCC_IXFI, d, n, 1 << 20, 1 << 20, 1, 0, n * d))
+        f.write(rows.tobytes())
+
+
+def read_flat_ip_file(path: str) -> np.ndarray:
+    with open(path, "rb") as f:
+        hdr = f.read(_HDR.size)
+        if len(hdr) != _HDR.size:
+            raise ValueError(f"{path}: truncated flat index header")
+        fourcc, d, n, _, _, _, metric, nfl = _HDR.unpack(hdr)
+        if fourcc != _FOURCC_IXFI:
+            raise ValueError(f"{path}: not an IndexFlatIP file (fourcc {fourcc:#x})")
+        if metric != 0 or nfl != n * d or d <= 0 or n < 0:
+            raise ValueError(f"{path}: inconsistent flat index header (d={d}, ntotal={n}, floats={nfl}, metric={metric})")
+        data = np.fromfile(f, dtype="<f4", count=n * d)
+    if data.size != n * d:
+        raise ValueError(f"{path}: truncated flat index payload")
+    return data.reshape(n, d)
+
+
+# ---------------------------------------------------------------------------------------------
+class FlatIPIndex:
+    """Device-resident exact inner-product index (stands where faiss.IndexFlatIP stood).
+
+    HBM layout: `xn` f32 [N, D] (what faiss would store) + `xh` bf16 [N, Dp] (streamed by the
+    tensor-core scan, Dp = D rounded up to 64) + `stats` f32 [4] (error-bound norms).
+    """
+
+    def __init__(self, d: int, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tt_b200 FlatIPIndex needs a CUDA device (there is no CPU search path)")
+        self.d = int(d)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.dp = int(_native.load().tt_flat_pitch(self.d))
+        self.xn: Optional[torch.Tensor] = None
+        self.xh: Optional[torch.Tensor] = None
+        self.stats = torch.zeros(4, device=self.device, dtype=torch.float32)
+        self.id_offset = 0
+        self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._exact_ws: Optional[torch.Tensor] = None
+        self._pinned: Dict[Tuple[str, int, int], torch.Tensor] = {}
+
+    # -- size ------------------------------------------------------------------------------
+    @property
+    def ntotal(self) -> int:
+        return 0 if self.xn is None else int(self.xn.shape[0])
+
+    # -- build -----------------------------------------------------------------------------
+    def _alloc(self, n: int) -> None:
+        xn = torch.empty((n, self.d), device=self.device, dtype=torch.float32)
+        xh = torch.empty((n, self.dp), device=self.device, dtype=torch.bfloat16)
+        old = self.ntotal
+        if old:
+            xn[:old].copy_(self.xn)
+            xh[:old].copy_(self.xh)
+        self.xn, self.xh = xn, xh
+        self._ws.clear()
+        self._exact_ws = None
+
+    def _build_rows(self, row0: int, rows: int, normalize: bool) -> None:
+        """Normalises xn[row0:row0+rows] in place and writes the bf16 shadow rows."""
+        lib = _native.load()
+        src = self.xn[row0:row0 + rows]
+        with torch.cuda.device(self.device):
+            _native.check(lib.tt_flat_build(src.data_ptr(), rows, self.d, 1 if normalize else 0,
+                                            self.xn.data_ptr(), self.xh.data_ptr(), row0, self.stats.data_ptr(),
+                                            ops._stream()), "tt_flat_build")
+
+    def add(self, x, normalize: bool = True, chunk_rows: int = 1 << 17) -> None:
+        """Appends rows (numpy [n,d] or a torch tensor on any device)."""
+        if isinstance(x, np.ndarray):
+            if x.ndim != 2 or x.shape[1] != self.d:
+                raise ValueError(f"expected [n, {self.d}] rows, got {x.shape}")
+            n = x.shape[0]
+            row0 = self.ntotal
+            self._alloc(row0 + n)
+            for s in range(0, n, chunk_rows):
+                e = min(n, s + chunk_rows)
+                host = torch.from_numpy(np.ascontiguousarray(x[s:e], dtype=np.float32))
+                self.xn[row0 + s:row0 + e].copy_(host, non_blocking=False)
+                self._build_rows(row0 + s, e - s, normalize)
+        else:
+            if x.dim() != 2 or x.shape[1] != self.d:
+                raise ValueError(f"expected [n, {self.d}] rows, got {tuple(x.shape)}")
+            n = x.shape[0]
+            row0 = self.ntotal
+            self._alloc(row0 + n)
+            for s in range(0, n, chunk_rows):
+                e = min(n, s + chunk_rows)
+                self.xn[row0 + s:row0 + e].copy_(x[s:e].to(torch.float32))
+                self._build_rows(row0 + s, e - s, normalize)
+
+    @classmethod
+    def adopt(cls, xn: torch.Tensor, normalize: bool = True, chunk_rows: int = 1 << 20) -> "FlatIPIndex":
+        """Takes ownership of a CUDA f32 [N,D] tensor and normalises it in place (no second fp32 copy;
+        used for catalogs generated or loaded directly on the device)."""
+        if not (xn.is_cuda and xn.dtype == torch.float32 and xn.dim() == 2 and xn.is_contiguous()):
+            raise ValueError("adopt() needs a contiguous CUDA float32 [N,D] tensor")
+        self = cls(xn.shape[1], xn.device)
+        self.xn = xn
+        self.xh = torch.empty((xn.shape[0], self.dp), device=xn.device, dtype=torch.bfloat16)
+        for s in range(0, xn.shape[0], chunk_rows):
+            self._build_rows(s, min(chunk_rows, xn.shape[0] - s), normalize)
+        return self
+
+    def rows_host(self) -> np.ndarray:
+        """The stored fp32 rows (what faiss.write_index would serialise)."""
+        return self.xn.cpu().numpy()
+
+    # -- search ----------------------------------------------------------------------------
+    def _workspace(self, nq: int, k: int) -> torch.Tensor:
+        key = (nq, k)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = int(_native.load().tt_flat_search_workspace_bytes(self.ntotal, self.d, nq, k))
+            ws = torch.empty(max(nbytes, 256), device=self.device, dtype=torch.uint8)
+            if len(self._ws) > 8:
+                self._ws.clear()
+            self._ws[key] = ws
+        return ws
+
+    def search_device(self, q: torch.Tensor, k: int):
+        """Asynchronous search of CUDA f32 queries [nq,D] on the current stream.
+
+        Returns (scores [nq,k] f32, ids [nq,k] i64, flags [nq] i32, n_uncertified [1] i32) device
+        tensors; rows with flags == 0 (see include/tt_b200.h) must be passed to `search_exact_device`.
+        """
+        if self.ntotal == 0:
+            raise ValueError("empty index")
+        if q.dim() != 2 or q.shape[1] != self.d:
+            raise ValueError(f"expected queries [nq, {self.d}], got {tuple(q.shape)}")
+        if not 1 <= k <= min(self.ntotal, _native.TT_FLAT_MAX_K):
+            raise ValueError(f"k must be in [1, min(ntotal, {_native.TT_FLAT_MAX_K})], got {k}")
+        q = ops._f32c(q, "queries")
+        nq = q.shape[0]
+        scores = torch.empty((nq, k), device=self.device, dtype=torch.float32)
+        ids = torch.empty((nq, k), device=self.device, dtype=torch.int64)
+        flags = torch.empty((max(nq, 1),), device=self.device, dtype=torch.int32)
+        nunc = torch.empty((1,), device=self.device, dtype=torch.int32)
+        ws = self._workspace(max(nq, 1), k)
+        with torch.cuda.device(self.device):
+            _native.check(_native.load().tt_flat_search(
+                q.data_ptr(), nq, self.xn.data_ptr(), self.xh.data_ptr(), self.stats.data_ptr(), self.ntotal, self.d,
+                k, self.id_offset, scores.data_ptr(), ids.data_ptr(), flags.data_ptr(), nunc.data_ptr(),
+                ws.data_ptr(), ws.numel(), ops._stream()), "tt_flat_search")
+        return scores, ids, flags[:nq], nunc
+
+    def search_exact_device(self, q: torch.Tensor, k: int, scores: Optional[torch.Tensor] = None,
+                            ids: Optional[torch.Tensor] = None, qsel: Optional[torch.Tensor] = None):
+        """Always-exact fp32 path; with `qsel` (i32 query rows) only those rows of scores/ids are rewritten."""
+        q = ops._f32c(q, "queries")
+        nq = q.shape[0]
+        if scores is None:
+            scores = torch.empty((nq, k), device=self.device, dtype=torch.float32)
+            ids = torch.empty((nq, k), device=self.device, dtype=torch.int64)
+        nsel = nq if qsel is None else int(qsel.numel())
+        lib = _native.load()
+        need = int(lib.tt_flat_search_exact_workspace_bytes(self.ntotal, self.d, nsel, k))
+        if self._exact_ws is None or self._exact_ws.numel() < need:
+            self._exact_ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        with torch.cuda.device(self.device):
+            _native.check(lib.tt_flat_search_exact(
+                q.data_ptr(), nq, 0 if qsel is None else qsel.data_ptr(), nsel, self.xn.data_ptr(), self.ntotal,
+                self.d, k, self.id_offset, scores.data_ptr(), ids.data_ptr(), self._exact_ws.data_ptr(),
+                self._exact_ws.numel(), ops._stream()), "tt_flat_search_exact")
+        return scores, ids
+
+    def scan_scores_device(self, q: torch.Tensor) -> torch.Tensor:
+        """Diagnostic: dense bf16 tensor-core scores [nq, N] exactly as the scan epilogue sees them
+        (tt_flat_scan_scores; small catalogs only).  Rows never reported by the kernel read NaN."""
+        q = ops._f32c(q, "queries")
+        nq = q.shape[0]
+        lib = _native.load()
+        need = int(lib.tt_flat_scan_scores_workspace_bytes(self.ntotal, self.d, nq))
+        ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        out = torch.empty((nq, self.ntotal), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _native.check(lib.tt_flat_scan_scores(q.data_ptr(), nq, self.xh.data_ptr(), self.stats.data_ptr(),
+                                                  self.ntotal, self.d, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  ops._stream()), "tt_flat_scan_scores")
+        return out
+
+    def search_checked_device(self, q: torch.Tensor, k: int):
+        """search_device + re-run of uncertified queries through the exact path (one host sync)."""
+        scores, ids, flags, nunc = self.search_device(q, k)
+        n_bad = int(nunc.item())
+        if n_bad:
+            qsel = torch.nonzero(flags == 0).flatten().to(torch.int32)
+            self.search_exact_device(q, k, scores, ids, qsel)
+        return scores, ids, n_bad
+
+    def _pin(self, tag: str, shape: Tuple[int, int], dtype) -> torch.Tensor:
+        key = (tag, shape[0], shape[1])
+        t = self._pinned.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+            if len(self._pinned) > 24:
+                self._pinned.clear()
+            self._pinned[key] = t
+        return t
+
+    def search(self, q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Host-to-host search, the shape of faiss `index.search(q, k)`: q f32 [nq,d] (un-normalised:
+        the device op applies q/(||q||+1e-8)) -> (scores f32 [nq,k], ids i64 [nq,k])."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.d:
+            raise ValueError(f"expected queries [nq, {self.d}], got {q.shape}")
+        nq = q.shape[0]
+        if nq == 0:
+            return np.empty((0, k), np.float32), np.empty((0, k), np.int64)
+        hq = self._pin("q", (nq, self.d), torch.float32)
+        hq.copy_(torch.from_numpy(q))
+        dq = hq.to(self.device, non_blocking=True)
+        scores, ids, _ = self.search_checked_device(dq, k)
+        hs = self._pin("s", (nq, k), torch.float32)
+        hi = self._pin("i", (nq, k), torch.int64)
+        hs.copy_(scores, non_blocking=True)
+        hi.copy_(ids, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return hs.numpy().copy(), hi.numpy().copy()
+
+
+# ---------------------------------------------------------------------------------------------
+class VectorDatabase:
+    """Vector database for product retrieval (reference vector_db.py:10)."""
+
+    def __init__(self, embedding_dim: int = 384):
+        self.embedding_dim = embedding_dim
+        self.index: Optional[FlatIPIndex] = None
+        self.product_ids: Optional[List[str]] = None
+        self.id_to_index: Optional[Dict[str, int]] = None
+        self.index_to_id: Optional[Dict[int, str]] = None
+
+    def build_index(self, embeddings: np.ndarray, product_ids: List[str]):
+        """vector_db.py:25-61 — rows are L2-normalised (x / (||x|| + 1e-8)) and stored as f32."""
+        n_products, dim = embeddings.shape
+        if dim != self.embedding_dim:
+            raise ValueError(f"Embedding dimension mismatch: expected {self.embedding_dim}, got {dim}")
+        index = FlatIPIndex(self.embedding_dim)
+        index.add(np.asarray(embeddings), normalize=True)
+        self.index = index
+        self.product_ids = product_ids
+        self.id_to_index = {pid: idx for idx, pid in enumerate(product_ids)}
+        self.index_to_id = {idx: pid for idx, pid in enumerate(product_ids)}
+        print(f"Built FAISS index with {n_products} products")
+
+    def load_index(self, index_path: str, product_ids_path: Optional[str] = None,
+                   mapping_path: Optional[str] = None):
+        """vector_db.py:63-98 — rows are taken verbatim from the file (no re-normalisation)."""
+        rows = read_flat_ip_file(index_path)
+        index = FlatIPIndex(rows.shape[1])
+        index.add(rows, normalize=False)
+        self.index = index
+        self.embedding_dim = rows.shape[1] if self.embedding_dim is None else self.embedding_dim
+        if product_ids_path:
+            self.product_ids = np.load(product_ids_path, allow_pickle=True).tolist()
+        else:
+            self.product_ids = [f"product_{i}" for i in range(self.index.ntotal)]
+        if mapping_path and Path(mapping_path).exists():
+            with open(mapping_path, "r", encoding="utf-8") as f:
+                self.id_to_index = json.load(f)
+            self.index_to_id = {v: k for k, v in self.id_to_index.items()}
+        else:
+            self.id_to_index = {pid: idx for idx, pid in enumerate(self.product_ids)}
+            self.index_to_id = {idx: pid for idx, pid in enumerate(self.product_ids)}
+        print(f"Loaded FAISS index with {len(self.product_ids)} products")
+
+    def save_index(self, index_path: str, product_ids_path: Optional[str] = None,
+                   mapping_path: Optional[str] = None):
+        """vector_db.py:100-128."""
+        if self.index is None:
+            raise ValueError("Index not built. Call build_index() first.")
+        write_flat_ip_file(index_path, self.index.rows_host())
+        if product_ids_path:
+            np.save(product_ids_path, np.array(self.product_ids))
+        if mapping_path and self.id_to_index:
+            with open(mapping_path, "w", encoding="utf-8") as f:
+                json.dump(self.id_to_index, f, ensure_ascii=False, indent=2)
+        print(f"Saved FAISS index to {index_path}")
+
+    # -- search --------------------------------------------------------------------------------
+    def search_batch(self, query_embeddings: np.ndarray, k: int = 10) -> Tuple[np.ndarray, np.ndarray]:
+        """Array-returning retrieval: (scores f32 [nq,k'], row indices i64 [nq,k']) with k' = min(k, ntotal)."""
+        if self.index is None:
+            raise ValueError("Index not built. Call build_index() or load_index() first.")
+        k = min(k, self.index.ntotal)   # vector_db.py:159
+        return self.index.search(np.asarray(query_embeddings), k)
+
+    def retrieve(self, query_embedding: np.ndarray, k: int = 10) -> List[Tuple[str, float]]:
+        """vector_db.py:130-169 — descending score; only query row 0 is returned, as in the reference."""
+        if self.index is None:
+            raise ValueError("Index not built. Call build_index() or load_index() first.")
+        query_embedding = np.asarray(query_embedding)
+        if query_embedding.ndim == 1:
+            query_embedding = query_embedding.reshape(1, -1)
+        scores, indices = self.search_batch(query_embedding, k)
+        results = []
+        for idx, score in zip(indices[0], scores[0]):
+            if 0 <= idx < len(self.product_ids):
+                results.append((self.product_ids[idx], float(score)))
+        return results
+
+    def retrieve_batch(self, query_embeddings: np.ndarray, k: int = 10) -> List[List[Tuple[str, float]]]:
+        """vector_db.py:171-209."""
+        if self.index is None:
+            raise ValueError("Index not built. Call build_index() or load_index() first.")
+        scores, indices = self.search_batch(query_embeddings, k)
+        pids = self.product_ids
+        n = len(pids)
+        all_results = []
+        for query_scores, query_indices in zip(scores.tolist(), indices.tolist()):
+            all_results.append([(pids[i], s) for i, s in zip(query_indices, query_scores) if 0 <= i < n])
+        return all_results
+
+    def get_embedding(self, product_id: str) -> Optional[np.ndarray]:
+        """vector_db.py:211-231 — the reference returns None in every branch; kept."""
+        return None
