@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the serving hot path: exact top-100 inner-product retrieval over a 10M x 384 catalog
+(BASELINE.json metric), sharded over N GPUs, plus buyer-tower pooling as a secondary line.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU port of the reference path (rank 0)
+
+A "step" is one search of a batch of `--nq` queries.  Prints ONE JSON line (rank 0).
+Catalog (7.68 GB of bf16 per pass, 15.4 GB fp32) is far larger than L2, so no flush is needed between
+iterations.  Inputs are synthetic (seeded N(0,1)), generated on the device per shard.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def max_over_ranks(ms: float, world: int) -> float:
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world: int):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def make_shard(n_total: int, d: int, world: int, rank: int):
+    """Catalog rows [lo,hi): i.i.d. N(0,1), seeded per 1M-row block so the catalog is the same for any N."""
+    import two_tower_model_v2_b200 as pkg
+    lo, hi = pkg.shard_bounds(n_total, world, rank)
+    xn = torch.empty((hi - lo, d), device="cuda", dtype=torch.float32)
+    blk = 1 << 20
+    g = torch.Generator(device="cuda")
+    b0 = lo // blk
+    r = lo
+    while r < hi:
+        b = r // blk
+        g.manual_seed(1234 + b)
+        block = torch.randn((min(blk, n_total - b * blk), d), device="cuda", generator=g)
+        s, e = r - b * blk, min(hi, (b + 1) * blk) - b * blk
+        xn[r - lo:r - lo + (e - s)].copy_(block[s:e])
+        r += e - s
+        del block
+    idx = pkg.FlatIPIndex.adopt(xn)
+    idx.id_offset = lo
+    return idx, lo, hi
+
+
+def bench_pooling(peaks, iters=20):
+    """Secondary metric: buyer encodes/s at BASELINE C2 (4096 buyers x 50 events x 384), both modes."""
+    import two_tower_model_v2_b200 as pkg
+    B, S, D = 4096, 50, 384
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = torch.randn((B, S, D), device="cuda", generator=g)
+    w = torch.tensor([1.0, 5.0, 10.0], device="cuda")[torch.multinomial(torch.tensor([0.75, 0.18, 0.07], device="cuda"), B * S, True, generator=g)].view(B, S)
+    out = {}
+    alg_bytes = B * S * D * 4 + B * S * 4 + B * D * 4
+    for method in ("weighted_avg", "attention"):
+        torch.manual_seed(0)
+        m = pkg.BuyerTower(D, method).cuda()
+        for _ in range(3):
+            m(x, w)
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            m(x, w)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        rec = {"buyer_encodes_per_s": B / (ms * 1e-3), "ms_per_batch": ms,
+               "hbm_gbs": alg_bytes / (ms * 1e-3) / 1e9, "hbm_frac": alg_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        if method == "attention":
+            flop = B * S * (2 * D * 128 + 2 * 128)
+            rec["fp32_tflops"] = flop / (ms * 1e-3) / 1e12
+        out[method] = rec
+    out["config"] = "4096 buyers x 50 events x 384 f32 (x 322 MB > L2)"
+    return out
+
+
+def cpu_baseline_search(n_total, d, nq, k, sample_rows=1 << 20, reps=2):
+    """CPU port of the reference search path (faiss-cpu IndexFlatIP is not installable: blocked fp32
+    sgemm + top-k, what faiss does for nq >= 20) on a bounded sample of the catalog, all host threads."""
+    from oracle import flat_ip_oracle as fo
+    sample_rows = min(sample_rows, n_total)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn((sample_rows, d), generator=g)
+    x = x / (x.norm(dim=1, keepdim=True) + 1e-8)
+    q = torch.randn((nq, d), generator=torch.Generator().manual_seed(4321))
+    q = q / (q.norm(dim=1, keepdim=True) + 1e-8)
+    best = float("inf")
+    for _ in range(reps):
+        t = time.perf_counter()
+        fo.torch_search(x, q, k)
+        best = min(best, time.perf_counter() - t)
+    scale = n_total / sample_rows
+    return {"value": nq / (best * scale), "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{nq} queries x top-{k} over {sample_rows} of {n_total} rows x {d} f32 (torch sgemm+topk port of "
+                      f"IndexFlatIP; faiss-cpu unavailable), time scaled x{scale:g}",
+            "seconds_per_sample_step": best, "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import flat_ip_oracle as fo
+    n_total, d, nq, k = args.catalog_rows, args.dim, args.nq, args.topk
+    sample_rows = min(1 << 20, n_total)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn((sample_rows, d), generator=g)
+    x = x / (x.norm(dim=1, keepdim=True) + 1e-8)
+    qs = torch.randn((args.warmup + args.steps, nq, d), generator=torch.Generator().manual_seed(4321))
+    for i in range(args.warmup):
+        fo.torch_search(x, qs[i] / (qs[i].norm(dim=1, keepdim=True) + 1e-8), k)
+    t = time.perf_counter()
+    for i in range(args.warmup, args.warmup + args.steps):
+        fo.torch_search(x, qs[i] / (qs[i].norm(dim=1, keepdim=True) + 1e-8), k)
+    el = time.perf_counter() - t
+    scale = n_total / sample_rows
+    ms_step = el / args.steps * 1e3 * scale
+    value = nq / (ms_step * 1e-3)
+    sample = (f"each step: {nq} queries x top-{k} over {sample_rows} of {n_total} rows (torch-CPU sgemm+topk port of "
+              f"faiss IndexFlatIP, faiss-cpu not installable), time scaled x{scale:g}")
+    line = {"impl": "reference", "metric": "exact top-100 queries/s, 10Mx384 catalog", "value": value,
+            "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"flat_ip_top{k}_{n_total}x{d}_nq{nq}", "catalog_rows": n_total, "dim": d,
+                       "topk": k, "query_batch": nq},
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nq", type=int, default=int(os.environ.get("TT_BENCH_NQ", "128")), help="queries per step")
+    ap.add_argument("--catalog-rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=384)
+    ap.add_argument("--topk", type=int, default=100)
+    ap.add_argument("--no-secondary", action="store_true", help="skip pooling / cpu baseline extras")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    world, rank, local = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    import two_tower_model_v2_b200 as pkg
+    from two_tower_model_v2_b200 import _native
+    lib = _native.load()
+    peaks = load_peaks()
+    n_total, d, nq, k = args.catalog_rows, args.dim, args.nq, args.topk
+
+    index, lo, hi = make_shard(n_total, d, world, rank)
+    n_local = hi - lo
+    sharded = pkg.ShardedFlatIPIndex(index, n_total) if world > 1 else None
+    total = args.warmup + args.steps
+    gq = torch.Generator(device="cuda").manual_seed(4321)
+    queries = torch.randn((total, nq, d), device="cuda", generator=gq)
+    queries_host = queries.cpu().numpy()
+
+    def step_device(i):
+        s, ids, flags, nunc = index.search_device(queries[i], min(k, n_local))
+        if world > 1:
+            from two_tower_model_v2_b200.sharded import gather_and_merge
+            s, ids = gather_and_merge(s, ids, pkg.ops.topk_merge)
+        return s, ids, nunc
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    launches0 = lib.tt_kernel_launch_count()
+    _native.check(lib.tt_profile_scan_arm(args.steps), "tt_profile_scan_arm")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nuncs = []
+    barrier(world)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for i in range(args.warmup, total):
+            nuncs.append(step_device(i)[2])
+        e1.record()
+        barrier(world)
+    ms_total = max_over_ranks(e0.elapsed_time(e1), world)
+    launches = lib.tt_kernel_launch_count() - launches0
+    scan_ms = (torch.empty(args.steps, dtype=torch.float32))
+    n_rec = lib.tt_profile_scan_read(scan_ms.data_ptr(), args.steps)
+    uncertified = int(torch.stack(nuncs).sum().item())
+    ms_step = ms_total / args.steps
+    value = nq / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (main scan) --------------------------------------------
+    dp = int(lib.tt_flat_pitch(d))
+    scan_avg_ms = float(scan_ms[:n_rec].mean()) if n_rec > 0 else None
+    alg_bytes = n_local * dp * 2 + nq * dp * 2           # bf16 catalog streamed once + the query block(s)
+    alg_flops = 2.0 * nq * n_local * d
+    crossover = (2 * d / (peaks["hbm_gbs"] * 1e9)) / (2 * d / (peaks["bf16_tflops"] * 1e12))
+    roofline = None
+    if scan_avg_ms:
+        gbs = alg_bytes / (scan_avg_ms * 1e-3) / 1e9
+        tfl = alg_flops / (scan_avg_ms * 1e-3) / 1e12
+        traffic = None
+        tp = ROOT / "profiles" / "scan_traffic.json"      # dram bytes/launch from the committed ncu capture
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get(f"nq{nq}")
+            except Exception:
+                traffic = None
+        if nq < crossover:
+            roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": gbs / peaks["hbm_gbs"], "traffic": traffic}
+        else:
+            roofline = {"bound": "tensor", "achieved": tfl, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": tfl / peaks["bf16_tflops_sustained"], "traffic": traffic}
+        roofline.update({"kernel": "flat_scan_kernel<main>", "kernel_ms": scan_avg_ms, "kernel_share_of_step": scan_avg_ms / ms_step,
+                         "algorithmic_bytes": alg_bytes, "algorithmic_flops": alg_flops, "hbm_gbs": gbs, "bf16_tflops": tfl,
+                         "peaks": peaks["source"], "crossover_nq": crossover})
+
+    # ---- end to end through the host-facing API (numpy in, numpy out) ----------------------------
+    def step_host(i):
+        if world == 1:
+            return index.search(queries_host[i], min(k, n_local))
+        hq = torch.from_numpy(queries_host[i]).pin_memory().cuda(non_blocking=True)
+        s, ids, _ = sharded.search_device(hq, k)
+        return s.cpu().numpy(), ids.cpu().numpy()
+
+    for i in range(min(2, args.warmup)):
+        step_host(i)
+    barrier(world)
+    t0 = time.perf_counter()
+    for i in range(args.warmup, total):
+        step_host(i)
+    barrier(world)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world) / args.steps
+    e2e = {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12 + 4,
+           "api": "FlatIPIndex.search(np.ndarray) (VectorDatabase.search_batch)" if world == 1 else "ShardedFlatIPIndex.search_device + host copies"}
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    line = {"metric": "exact top-100 queries/s, 10Mx384 catalog", "value": value, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 scan + f32 rescoring",
+            "data": "synthetic",
+            "config": {"workload": f"flat_ip_top{k}_{n_total}x{d}_nq{nq}", "catalog_rows": n_total, "dim": d, "topk": k,
+                       "query_batch": nq, "sharding": f"catalog rows over {world} GPU(s), all-gather + merge" if world > 1 else "none",
+                       "l2": "inputs (7.68 GB bf16 per pass) exceed L2; no flush"},
+            "e2e": e2e, "gpu_launches": int(launches), "uncertified_queries": uncertified,
+            "roofline": roofline, "clocks": clk.summary()}
+    if world == 1 and not args.no_secondary:
+        line["secondary"] = {"pooling": bench_pooling(peaks)}
+        line["cpu_baseline"] = cpu_baseline_search(n_total, d, nq, k)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,14 @@ int tt_flat_search_exact(const float* q, int nq, const int32_t* qsel, int nsel,
 int tt_topk_merge(const float* scores_g, const int64_t* ids_g, int G, int nq, int K,
                   float* scores, int64_t* ids, void* stream);
 
+/* Measurement hooks (bench.py).  tt_kernel_launch_count: kernels this library has launched in this
+ * process.  tt_profile_scan_arm(n): the next n main-scan launches of tt_flat_search are bracketed by
+ * CUDA events on their stream; tt_profile_scan_read: waits for them, writes their durations in ms,
+ * returns how many were recorded (-1 on a CUDA error) and disarms. */
+int64_t tt_kernel_launch_count(void);
+int tt_profile_scan_arm(int max_records);
+int tt_profile_scan_read(float* ms_out, int max_out);
+
 /* Diagnostic / parity-test entry: the raw bf16 tensor-core scores of EVERY row of a small catalog
  * (N <= 2^22), out f32 [nq, N] = <bf16(qn), Xh[r]> with fp32 accumulation, as the scan kernel's
  * epilogue sees them.  Runs the same kernel as tt_flat_search with the threshold at -inf. */

@@ -1,10 +1,25 @@
 // C-ABI glue: error reporting and the tt_flat_search orchestration (include/tt_b200.h).
 #include "tt_common.cuh"
 #include "flat_internal.cuh"
+#include <atomic>
+#include <vector>
 
 namespace tt {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// scan-kernel timing records (armed by tt_profile_scan_arm)
+static std::vector<cudaEvent_t> g_ev;     // 2 events per record
+static int g_prof_cap = 0, g_prof_n = 0;
+void profile_scan_begin(cudaStream_t st) {
+  if (g_prof_n < g_prof_cap) cudaEventRecord(g_ev[2 * g_prof_n], st);
+}
+void profile_scan_end(cudaStream_t st) {
+  if (g_prof_n < g_prof_cap) { cudaEventRecord(g_ev[2 * g_prof_n + 1], st); ++g_prof_n; }
+}
 
 struct SearchWs {
   size_t qn, qh, eps, thr, cnt, cand, sample, total;
@@ -29,6 +44,30 @@ using namespace tt;
 
 extern "C" __attribute__((visibility("default"))) int tt_abi_version(void) { return TT_B200_ABI_VERSION; }
 extern "C" __attribute__((visibility("default"))) const char* tt_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" __attribute__((visibility("default"))) int64_t tt_kernel_launch_count(void) { return g_launches.load(); }
+
+extern "C" __attribute__((visibility("default"))) int tt_profile_scan_arm(int max_records) {
+  TT_CHECK_ARG(max_records >= 0 && max_records <= 4096, "max_records out of range");
+  while ((int)g_ev.size() < 2 * max_records) {
+    cudaEvent_t e;
+    TT_CHECK_CUDA(cudaEventCreate(&e));
+    g_ev.push_back(e);
+  }
+  g_prof_cap = max_records;
+  g_prof_n = 0;
+  return TT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_profile_scan_read(float* ms_out, int max_out) {
+  int n = g_prof_n < max_out ? g_prof_n : max_out;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(g_ev[2 * i + 1]) != cudaSuccess) return -1;
+    if (cudaEventElapsedTime(ms_out + i, g_ev[2 * i], g_ev[2 * i + 1]) != cudaSuccess) return -1;
+  }
+  g_prof_cap = 0;
+  return n;
+}
 
 extern "C" __attribute__((visibility("default"))) size_t tt_flat_search_workspace_bytes(int64_t N, int D, int nq, int K) {
   if (N < 1 || D < 1 || nq < 1 || K < 1) return 0;

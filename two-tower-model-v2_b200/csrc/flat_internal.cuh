@@ -37,4 +37,9 @@ int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long l
                     const void* cand, float* scores, long long* ids, int* flags, int* n_uncertified,
                     cudaStream_t st);
 
+// Optional device-side timing of the main scan kernel (bench.py roofline): when armed, launch_scan
+// brackets the main scan launch with a pair of CUDA events on the launching stream.
+void profile_scan_begin(cudaStream_t st);
+void profile_scan_end(cudaStream_t st);
+
 }  // namespace tt

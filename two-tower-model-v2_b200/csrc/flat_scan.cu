@@ -445,8 +445,11 @@ int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N,
   }
   sp.num_slots = pl.num_tiles; sp.tile_stride = 1;
   const int grid = pl.main_slices * pl.nqb;
-  return (pl.block_m == 128) ? launch_scan_t<128, false>(tq, tx, sp, grid, pl.smem_bytes, st)
-                             : launch_scan_t<64, false>(tq, tx, sp, grid, pl.smem_bytes, st);
+  profile_scan_begin(st);
+  const int e = (pl.block_m == 128) ? launch_scan_t<128, false>(tq, tx, sp, grid, pl.smem_bytes, st)
+                                    : launch_scan_t<64, false>(tq, tx, sp, grid, pl.smem_bytes, st);
+  profile_scan_end(st);
+  return e;
 }
 
 }  // namespace tt

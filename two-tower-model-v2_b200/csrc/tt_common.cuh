@@ -32,7 +32,12 @@ void set_error(const std::string& msg);   // defined in api.cu (thread-local)
     }                                                                               \
   } while (0)
 
-#define TT_CHECK_LAUNCH() TT_CHECK_CUDA(cudaGetLastError())
+void count_launch();                      // api.cu: kernels launched by this library (process-wide)
+#define TT_CHECK_LAUNCH()                 \
+  do {                                    \
+    ::tt::count_launch();                 \
+    TT_CHECK_CUDA(cudaGetLastError());    \
+  } while (0)
 
 inline int num_sms() {
   static int n = 0;
