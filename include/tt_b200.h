@@ -155,6 +155,11 @@ int64_t tt_kernel_launch_count(void);
 int tt_profile_scan_arm(int max_records);
 int tt_profile_scan_read(float* ms_out, int max_out);
 
+/* Host-only: the planner's decisions for (N, D, nq, K) as 16 ints: supported, block_m, k_blocks,
+ * stages, query_blocks, tiles, use_threshold, route_exact, target_candidates, candidate_capacity,
+ * sample_stride, sample_slots, sample_rank, main_slices, sample_slices, smem_bytes. */
+int tt_flat_plan_describe(int64_t N, int D, int nq, int K, int32_t* out16);
+
 /* Diagnostic / parity-test entry: the raw bf16 tensor-core scores of EVERY row of a small catalog
  * (N <= 2^22), out f32 [nq, N] = <bf16(qn), Xh[r]> with fp32 accumulation, as the scan kernel's
  * epilogue sees them.  Runs the same kernel as tt_flat_search with the threshold at -inf. */

@@ -88,3 +88,34 @@ def test_shard_bounds_cover_catalog():
         assert all(0 <= hi - lo <= -(-n // g) for lo, hi in spans)
     with pytest.raises(ValueError):
         pkg.shard_bounds(10, 2, 2)
+
+
+def _plan(N, D, nq, K):
+    import ctypes
+    from two_tower_model_v2_b200 import _native
+    out = (ctypes.c_int32 * 16)()
+    _native.check(_native.load().tt_flat_plan_describe(N, D, nq, K, out), "tt_flat_plan_describe")
+    names = ("supported block_m k_blocks stages query_blocks tiles use_threshold route_exact target cap "
+             "stride slots rank main_slices sample_slices smem").split()
+    return dict(zip(names, out))
+
+
+def test_search_planner_invariants():
+    """The host-side planner (no GPU needed): smem budget, tiling and candidate-budget routing."""
+    for N, D, nq, K in [(10_000_000, 384, 128, 100), (1_000_000, 384, 4096, 100), (100_000_000, 384, 1, 100),
+                        (10_000_000, 768, 64, 100), (20_000, 384, 2000, 10), (9_000, 64, 16, 1000),
+                        (70_000, 256, 40, 500), (2_049, 32, 9, 100), (1, 8, 1, 1), (12_500_000, 384, 1024, 1000)]:
+        p = _plan(N, D, nq, K)
+        assert p["supported"] == 1 and p["smem"] <= 227 * 1024 and p["stages"] >= 2
+        assert p["block_m"] == (128 if D <= 512 else 64)
+        assert p["k_blocks"] == -(-D // 64) and p["tiles"] == -(-N // 256)
+        assert p["query_blocks"] == -(-nq // p["block_m"])
+        assert 1 <= p["main_slices"] <= p["tiles"] and p["main_slices"] * p["query_blocks"] <= max(148, p["query_blocks"])
+        assert not (p["use_threshold"] and p["route_exact"])
+        if p["use_threshold"]:
+            assert p["target"] >= 2 * K and p["cap"] >= 4 * p["target"] or p["cap"] == 16384
+            assert 1 <= p["rank"] <= p["slots"] * 8 // 2 and p["slots"] <= 4096
+        elif not p["route_exact"]:
+            assert p["cap"] >= N            # every row is a candidate and must fit the list
+    assert _plan(10_000_000, 384, 128, 100)["use_threshold"] == 1
+    assert _plan(9_000, 64, 16, 1000)["use_threshold"] == 0

@@ -34,7 +34,7 @@ static SearchWs search_ws_layout(const ScanPlan& pl, int D, int nq) {
   w.thr = o;    o += align_up((size_t)nq * sizeof(float), 256);
   w.cnt = o;    o += align_up((size_t)nq * sizeof(unsigned int), 256);
   w.cand = o;   o += align_up((size_t)nq * pl.cand_cap * 8, 256);
-  w.sample = o; o += align_up((size_t)pl.sample_slices * pl.nq_pad * SAMPLE_R * sizeof(float), 256);
+  w.sample = o; o += align_up((size_t)pl.sample_slots * 8 * pl.nq_pad * sizeof(float), 256);
   w.total = o;
   return w;
 }
@@ -69,9 +69,15 @@ extern "C" __attribute__((visibility("default"))) int tt_profile_scan_read(float
   return n;
 }
 
+__global__ void fill_int_kernel(int* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 extern "C" __attribute__((visibility("default"))) size_t tt_flat_search_workspace_bytes(int64_t N, int D, int nq, int K) {
   if (N < 1 || D < 1 || nq < 1 || K < 1) return 0;
   const ScanPlan pl = make_scan_plan(N, D, nq, K);
+  if (pl.route_exact) return tt_flat_search_exact_workspace_bytes(N, D, nq, K);
   return search_ws_layout(pl, D, nq).total;
 }
 
@@ -94,8 +100,16 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_search(const float
     set_error("tt_flat_search: embedding dimension too large for the resident-query scan (D <= 1024 supported)");
     return TT_ERR_UNSUPPORTED;
   }
-  const SearchWs w = search_ws_layout(pl, D, nq);
   TT_CHECK_ARG(workspace != nullptr, "null workspace");
+  TT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  if (pl.route_exact) {
+    // K is too large a fraction of N for a sampled threshold: the fp32 exact path serves the batch.
+    fill_int_kernel<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, 1);
+    TT_CHECK_LAUNCH();
+    return tt_flat_search_exact(q, nq, nullptr, nq, Xn, N, D, K, id_offset, scores, ids, workspace,
+                                workspace_bytes, stream);
+  }
+  const SearchWs w = search_ws_layout(pl, D, nq);
   if (workspace_bytes < w.total) { set_error("tt_flat_search: workspace too small"); return TT_ERR_WORKSPACE; }
   TT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
@@ -132,6 +146,7 @@ extern "C" __attribute__((visibility("default"))) size_t tt_flat_scan_scores_wor
   if (N < 1 || D < 1 || nq < 1) return 0;
   ScanPlan pl = make_scan_plan(N, D, nq, 1);
   pl.use_threshold = false;
+  pl.route_exact = false;
   pl.cand_cap = (int)N;
   return search_ws_layout(pl, D, nq).total;
 }
@@ -144,6 +159,7 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_scan_scores(const 
   ScanPlan pl = make_scan_plan(N, D, nq, 1);
   if (!pl.supported) { set_error("tt_flat_scan_scores: D too large"); return TT_ERR_UNSUPPORTED; }
   pl.use_threshold = false;
+  pl.route_exact = false;
   pl.cand_cap = (int)N;
   const SearchWs w = search_ws_layout(pl, D, nq);
   if (workspace_bytes < w.total) { set_error("tt_flat_scan_scores: workspace too small"); return TT_ERR_WORKSPACE; }
@@ -161,5 +177,16 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_scan_scores(const 
   if (int e = launch_scan(pl, qh, Xh, N, nq, thr, cnt, cand, sample, st)) return e;
   scatter_scores_kernel<<<dim3(64, nq), 256, 0, st>>>(cnt, reinterpret_cast<const uint2*>(cand), pl.cand_cap, N, out);
   TT_CHECK_LAUNCH();
+  return TT_OK;
+}
+
+// Host-only: the decisions tt_flat_search would take for (N, D, nq, K); lets CPU tests check the planner.
+extern "C" __attribute__((visibility("default"))) int tt_flat_plan_describe(int64_t N, int D, int nq, int K, int32_t* out16) {
+  TT_CHECK_ARG(out16 != nullptr && N >= 1 && D >= 1 && nq >= 1 && K >= 1, "bad argument");
+  const ScanPlan pl = make_scan_plan(N, D, nq, K);
+  const int32_t v[16] = {pl.supported, pl.block_m, pl.num_kb, pl.num_stages, pl.nqb, pl.num_tiles, pl.use_threshold,
+                         pl.route_exact, pl.target, pl.cand_cap, pl.sample_stride, pl.sample_slots, pl.sample_rank,
+                         pl.main_slices, pl.sample_slices, (int32_t)pl.smem_bytes};
+  for (int i = 0; i < 16; ++i) out16[i] = v[i];
   return TT_OK;
 }

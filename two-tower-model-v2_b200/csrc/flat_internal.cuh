@@ -6,7 +6,7 @@
 
 namespace tt {
 
-constexpr int SAMPLE_R = 32;               // per-thread top-R kept by the sample pass
+constexpr int SAMPLE_MAX_SLOTS = 4096;      // sampled tiles per query (8 chunk maxima each are staged in smem)
 constexpr int FINALIZE_MAX_CAND = 16384;   // candidates per query the finalize kernel can sort (128 KiB smem)
 
 // Everything the host decides about one search call (pure function of N, D, nq, K and the SM count).
@@ -17,7 +17,8 @@ struct ScanPlan {
   int nqb, nq_pad, num_tiles;
   int target;          // expected candidates per query
   int cand_cap;        // capacity of a query's candidate list
-  bool use_threshold;  // false: catalog small enough that every row is a candidate
+  bool use_threshold;  // false: every row is a candidate (small catalogs)
+  bool route_exact;    // true: K is too large a fraction of N for a sampled threshold -> fp32 exact path
   int main_slices;
   int sample_stride, sample_slots, sample_slices, sample_rank;
 };

@@ -22,12 +22,13 @@
 // blocks.
 //
 // Two epilogue modes:
-//   SAMPLE : scan every `tile_stride`-th tile and keep the per-thread top-R scores in registers;
-//            tt::select_thresholds turns them into a per-query threshold that is a guaranteed
-//            lower bound of the K-th best bf16 score (the r-th best of a subset never exceeds
-//            the r-th best of the whole).
+//   SAMPLE : scan every `tile_stride`-th tile and write only the maximum score of each 32-row
+//            chunk per query; select_threshold_kernel takes the r-th largest of those maxima as
+//            the query's threshold.  Chunk maxima are scores of distinct rows, so the threshold
+//            is a guaranteed lower bound of the r-th best bf16 score of the whole catalog.
 //   MAIN   : scan every tile, append scores >= threshold.
 #include <cuda.h>
+#include <math.h>
 #include "tt_common.cuh"
 #include "sm100_ptx.cuh"
 #include "flat_internal.cuh"
@@ -58,7 +59,7 @@ struct ScanParams {
   uint2* cand;            // [nq, cand_cap]  (score bits, row)
   int cand_cap;
   // SAMPLE
-  float* sample_out;      // [nslices, nq_pad, SAMPLE_R]
+  float* sample_out;      // [nq_pad, num_slots, 8] maxima of the 32-row chunks of every sampled tile
   int nq_pad;
 };
 
@@ -184,13 +185,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const bool valid = (q_local >= 0) && (q < p.nq);
 
     float thr = INFINITY;
-    float top[SAMPLE ? SAMPLE_R : 1];
-    if (SAMPLE) {
-#pragma unroll
-      for (int i = 0; i < (SAMPLE ? SAMPLE_R : 1); ++i) top[i] = -INFINITY;
-    } else {
-      if (valid) thr = __ldg(p.thr + q);
-    }
+    if (!SAMPLE && valid) thr = __ldg(p.thr + q);
     unsigned int* my_cnt = SAMPLE ? nullptr : (p.cand_cnt + (valid ? q : 0));
     uint2* my_cand = SAMPLE ? nullptr : (p.cand + (size_t)(valid ? q : 0) * p.cand_cap);
 
@@ -203,33 +198,23 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_wait(smem_u32(tmem_full_bar + buf), use_phase, 300 + buf);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BLOCK_N);
-#pragma unroll 1
+      float cmax[BLOCK_N / 32];   // SAMPLE: maximum of each 32-row chunk of this tile
+#pragma unroll
+      for (int c = 0; c < BLOCK_N / 32; ++c) cmax[c] = -INFINITY;
+#pragma unroll
       for (int c = 0; c < BLOCK_N / 32; ++c) {
-        if (c * 32 >= ncols) break;                    // warp-uniform
+        if (c * 32 >= ncols) continue;                 // warp-uniform (partial last tile)
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
         tmem_ld_wait();
         const int limit = ncols - c * 32;              // >= 1; columns >= limit are padding rows
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, (j < limit) ? __uint_as_float(v[j]) : -INFINITY);
         if (SAMPLE) {
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float s = __uint_as_float(v[j]);
-              if (j < limit && s > top[SAMPLE_R - 1]) {
-#pragma unroll
-                for (int i = 0; i < SAMPLE_R; ++i) {
-                  const float hi = fmaxf(top[i], s);
-                  s = fminf(top[i], s);
-                  top[i] = hi;
-                }
-              }
-            }
-          }
+          cmax[c] = m;
         } else {
-          float m = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) m = fmaxf(m, (j < limit) ? __uint_as_float(v[j]) : -INFINITY);
           if (m >= thr) {                              // rare: some column of this chunk qualifies
             const uint32_t rbase = (uint32_t)row0 + (uint32_t)(c * 32);
 #pragma unroll
@@ -247,12 +232,11 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(tmem_empty_bar + buf));
-    }
-
-    if (SAMPLE && valid) {
-      float* o = p.sample_out + ((size_t)slice * p.nq_pad + q) * SAMPLE_R;
-#pragma unroll
-      for (int i = 0; i < SAMPLE_R; ++i) o[i] = top[i];
+      if (SAMPLE && valid) {
+        float4* o = reinterpret_cast<float4*>(p.sample_out + ((size_t)q * p.num_slots + (slot_begin + t)) * (BLOCK_N / 32));
+        o[0] = make_float4(cmax[0], cmax[1], cmax[2], cmax[3]);
+        o[1] = make_float4(cmax[4], cmax[5], cmax[6], cmax[7]);
+      }
     }
   }
 
@@ -266,21 +250,35 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
-// thr[q] = r-th largest of the sampled scores of query q (over all slices); -inf if fewer.
-// One CTA per query, values staged in shared memory, r rounds of block-wide arg-max.
+// thr[q] = r-th largest of the sampled chunk maxima of query q; -inf if there are fewer than r.
+// One CTA per query, values staged in shared memory; r rounds of block-wide arg-max for small r,
+// a bitonic sort otherwise.
 __global__ void __launch_bounds__(256)
-select_threshold_kernel(const float* __restrict__ sample, int nslices, int nq_pad, int nq, int r, float* thr) {
+select_threshold_kernel(const float* __restrict__ sample, int n, int npad, int r, float* thr) {
   extern __shared__ float vals[];
   __shared__ float wmax[8];
   __shared__ int widx[8];
   __shared__ float result;
   const int q = blockIdx.x;
-  const int n = nslices * SAMPLE_R;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int s = i / SAMPLE_R, k = i % SAMPLE_R;
-    vals[i] = sample[((size_t)s * nq_pad + q) * SAMPLE_R + k];
-  }
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) vals[i] = (i < n) ? sample[(size_t)q * n + i] : -INFINITY;
   __syncthreads();
+  if (r > 64) {
+    for (int k = 2; k <= npad; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const float a = vals[i], b = vals[ixj];
+            const bool up = (i & k) == 0;
+            if (up ? (a < b) : (a > b)) { vals[i] = b; vals[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (threadIdx.x == 0) thr[q] = (r <= n) ? vals[r - 1] : -INFINITY;
+    return;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int round = 0; round < r; ++round) {
     float best = -INFINITY;
@@ -366,46 +364,80 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   pl.nq_pad = pl.nqb * pl.block_m;
   pl.num_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
 
-  // candidate budget: target T candidates per query, capacity C
-  int T = 4 * K;
-  if (T < 512) T = 512;
-  pl.target = T;
-  int C = 4096;
-  while (C < 4 * T) C <<= 1;
-  if (C > FINALIZE_MAX_CAND) C = FINALIZE_MAX_CAND;
-  pl.use_threshold = N > (long long)C / 2;
-  if (!pl.use_threshold) { while (C < N) C <<= 1; }
-  pl.cand_cap = C;
-
   const int sms = num_sms();
-  // main scan grid: nqb query blocks x nslices catalog slices
   int ns = sms / pl.nqb;
   if (ns < 1) ns = 1;
   if (ns > pl.num_tiles) ns = pl.num_tiles;
   pl.main_slices = ns;
 
-  // sample pass
-  pl.sample_stride = T / 16;
-  if (pl.sample_stride < 1) pl.sample_stride = 1;
-  pl.sample_slots = (pl.num_tiles + pl.sample_stride - 1) / pl.sample_stride;
+  // Candidate budget and sampling plan.  We aim at ~T candidates per query: the threshold is read
+  // among the 32-row chunk maxima of every `stride`-th tile at the rank r' = T * n_s / N (n_s =
+  // sampled rows) corrected for chunk collisions.  r' >= 12 keeps the sampling noise of the
+  // candidate count near +-30%.
+  auto try_plan = [&](int T, int stride) -> bool {
+    if (stride < 1) stride = 1;
+    long long slots = (pl.num_tiles + stride - 1) / stride;
+    if (slots > SAMPLE_MAX_SLOTS) return false;
+    const long long last_slot = slots - 1;
+    long long rem = N - last_slot * (long long)stride * BLOCK_N;
+    if (rem > BLOCK_N) rem = BLOCK_N;
+    const long long ns_rows = last_slot * BLOCK_N + rem;
+    // r' = rank (within the sample) of the score that ~T rows of the whole catalog reach
+    const double rp = (double)T * (double)ns_rows / (double)N;
+    const double nvals = (double)(slots * (BLOCK_N / 32));
+    if (rp < 11.5 || rp > 0.7 * nvals) return false;
+    // The top-r' sampled rows occupy about nvals*(1-exp(-r'/nvals)) distinct 32-row chunks, so that is
+    // the rank to read among the chunk maxima (a smaller rank would only over-fetch; never unsafe).
+    const double r = nvals * (1.0 - exp(-rp / nvals));
+    pl.target = T;
+    pl.sample_stride = stride;
+    pl.sample_slots = (int)slots;
+    pl.sample_rank = (int)(r + 0.5) < 1 ? 1 : (int)(r + 0.5);
+    return true;
+  };
+  bool reliable = false;
+  const int Tmax = FINALIZE_MAX_CAND / 4;
+  {
+    int T = 4 * K < 128 ? 128 : 4 * K;
+    if (T > Tmax) T = Tmax;
+    // (a) the usual case: r ~ 16 from a sparse sample
+    reliable = try_plan(T, T / 16);
+    // (b) huge catalogs: the slot cap forces a sparser sample; raise T so that r stays >= 12
+    if (!reliable && (pl.num_tiles + (T / 16 > 0 ? T / 16 : 1) - 1) / (T / 16 > 0 ? T / 16 : 1) > SAMPLE_MAX_SLOTS) {
+      const int stride = (pl.num_tiles + SAMPLE_MAX_SLOTS - 1) / SAMPLE_MAX_SLOTS;
+      for (int T2 = T; T2 <= Tmax && !reliable; T2 += T2 / 4 + 1) reliable = try_plan(T2, stride);
+    }
+    // (c) small catalogs / large K: denser samples, down to every tile, and a leaner budget
+    const int T_lean = (2 * K + 64 < 128) ? 128 : 2 * K + 64;
+    for (int stride = T / 32; !reliable && stride >= 1; stride /= 2) reliable = try_plan(T, stride);
+    if (!reliable && T_lean < T && T_lean <= Tmax)
+      for (int stride = T_lean / 16; !reliable; stride /= 2) {
+        reliable = try_plan(T_lean, stride);
+        if (stride <= 1) break;
+      }
+  }
+  int C = 4096;
+  if (reliable) while (C < 4 * pl.target) C <<= 1;
+  if (C > FINALIZE_MAX_CAND) C = FINALIZE_MAX_CAND;
+
+  // Routing: threshold path when the estimate is trustworthy; otherwise every row is a candidate
+  // if the catalog fits a candidate list, else the always-exact fp32 path.
+  pl.route_exact = false;
+  pl.use_threshold = reliable;
+  if (!reliable) {
+    pl.sample_stride = 1; pl.sample_slots = 1; pl.sample_rank = 1; pl.target = 0;
+    if (N <= FINALIZE_MAX_CAND) {
+      C = 2048;
+      while (C < N) C <<= 1;
+    } else {
+      pl.route_exact = true;
+    }
+  }
   int ss = sms / pl.nqb;
   if (ss < 1) ss = 1;
   if (ss > pl.sample_slots) ss = pl.sample_slots;
   pl.sample_slices = ss;
-  // rows actually covered by the sampled tiles
-  long long ns_rows = 0;
-  {
-    const long long last_slot = pl.sample_slots - 1;
-    ns_rows = last_slot * BLOCK_N;
-    const long long last_row0 = last_slot * (long long)pl.sample_stride * BLOCK_N;
-    long long rem = N - last_row0;
-    if (rem > BLOCK_N) rem = BLOCK_N;
-    ns_rows += rem;
-  }
-  long long r = (long long)((double)T * (double)ns_rows / (double)N);
-  if (r < 1) r = 1;
-  if (r > SAMPLE_R) r = SAMPLE_R;
-  pl.sample_rank = (int)r;
+  pl.cand_cap = C;
   return pl;
 }
 
@@ -436,8 +468,12 @@ int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N,
     int e = (pl.block_m == 128) ? launch_scan_t<128, true>(tq, tx, sp, grid, pl.smem_bytes, st)
                                 : launch_scan_t<64, true>(tq, tx, sp, grid, pl.smem_bytes, st);
     if (e) return e;
-    const size_t sm = (size_t)pl.sample_slices * SAMPLE_R * sizeof(float);
-    select_threshold_kernel<<<nq, 256, sm, st>>>(sample_buf, pl.sample_slices, pl.nq_pad, nq, pl.sample_rank, thr);
+    const int nvals = pl.sample_slots * (BLOCK_N / 32);
+    int npad = 1;
+    while (npad < nvals) npad <<= 1;
+    const size_t sm = (size_t)npad * sizeof(float);
+    TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    select_threshold_kernel<<<nq, 256, sm, st>>>(sample_buf, nvals, npad, pl.sample_rank, thr);
     TT_CHECK_LAUNCH();
   } else {
     fill_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thr, nq, -INFINITY);

@@ -54,7 +54,7 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ qs, const fl
 
 // ------------------------------------------------------------------------------------------
 // finalize: one CTA per query
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn, long long N, int D, int K,
                      long long id_offset, const float* __restrict__ thr, const float* __restrict__ eps,
                      const unsigned int* __restrict__ cand_cnt, const uint2* __restrict__ cand, int cand_cap,
@@ -76,17 +76,54 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
   const uint2* mine = cand + (size_t)q * cand_cap;
   const float my_eps = eps[q];
   int bad = 0;   // self-check: a candidate's tensor-core score must match its fp32 rescoring within eps
-  for (int i = warp; i < n; i += nwarps) {
-    const uint2 c = mine[i];
-    const uint32_t row = c.y;
-    if ((long long)row >= N) {            // cannot happen unless the scan is broken
-      if (lane == 0) { key[i] = 0ull; bad = 1; }
-      continue;
+  constexpr int U = 4;   // candidates rescored concurrently per warp (independent loads in flight)
+  for (int i0 = warp * U; i0 < n; i0 += nwarps * U) {
+    uint2 c[U];
+    bool ok[U];
+    float a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u;
+      c[u] = (i < n) ? mine[i] : make_uint2(0u, 0xffffffffu);
+      ok[u] = (i < n) && ((long long)c[u].y < N);   // row >= N cannot happen unless the scan is broken
+      a[u] = 0.f;
     }
-    const float s = warp_dot(qs, Xn + (long long)row * D, D, lane, vec);
-    if (lane == 0) {
-      key[i] = make_key(s, row);
-      if (!(fabsf(__uint_as_float(c.x) - s) <= my_eps)) bad = 1;
+    if (vec) {
+      const float4* q4 = reinterpret_cast<const float4*>(qs);
+      for (int cc = lane; cc < (D >> 2); cc += 32) {
+        const float4 y = q4[cc];
+        float4 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          x[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(Xn + (long long)c[u].y * D) + cc)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          a[u] = fmaf(x[u].x, y.x, a[u]); a[u] = fmaf(x[u].y, y.y, a[u]);
+          a[u] = fmaf(x[u].z, y.z, a[u]); a[u] = fmaf(x[u].w, y.w, a[u]);
+        }
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) {
+        const float y = qs[d];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (ok[u]) a[u] = fmaf(__ldg(Xn + (long long)c[u].y * D + d), y, a[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float sc = warp_sum(a[u]);
+      const int i = i0 + u;
+      if (lane == 0 && i < n) {
+        if (ok[u]) {
+          key[i] = make_key(sc, c[u].y);
+          if (!(fabsf(__uint_as_float(c[u].x) - sc) <= my_eps)) bad = 1;
+        } else {
+          key[i] = 0ull;
+          bad = 1;
+        }
+      }
     }
   }
   for (int i = n + threadIdx.x; i < P; i += blockDim.x) key[i] = 0ull;
@@ -120,7 +157,7 @@ int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long l
                     cudaStream_t st) {
   const size_t smem = (size_t)pl.cand_cap * 8 + (size_t)D * 4 + 16;
   TT_CHECK_CUDA(cudaFuncSetAttribute(flat_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  flat_finalize_kernel<<<nq, 256, smem, st>>>(qn, Xn, N, D, K, id_offset, thr, eps, cand_cnt,
+  flat_finalize_kernel<<<nq, 512, smem, st>>>(qn, Xn, N, D, K, id_offset, thr, eps, cand_cnt,
                                               reinterpret_cast<const uint2*>(cand), pl.cand_cap, scores, ids, flags,
                                               n_uncertified);
   TT_CHECK_LAUNCH();
