@@ -114,7 +114,7 @@ def test_search_planner_invariants():
         assert not (p["use_threshold"] and p["route_exact"])
         if p["use_threshold"]:
             assert p["target"] >= 2 * K and p["cap"] >= 4 * p["target"] or p["cap"] == 16384
-            assert 1 <= p["rank"] <= p["slots"] * 8 // 2 and p["slots"] <= 4096
+            assert 1 <= p["rank"] <= p["slots"] * 8 and p["slots"] <= 4096
         elif not p["route_exact"]:
             assert p["cap"] >= N            # every row is a candidate and must fit the list
     assert _plan(10_000_000, 384, 128, 100)["use_threshold"] == 1

@@ -251,14 +251,14 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
 // ------------------------------------------------------------------------------------------
 // thr[q] = r-th largest of the sampled chunk maxima of query q; -inf if there are fewer than r.
-// One CTA per query, values staged in shared memory; r rounds of block-wide arg-max for small r,
-// a bitonic sort otherwise.
+// One CTA per query, values staged in shared memory.  Small r: r rounds of block-wide arg-max where
+// every thread caches the best of its own strided values and only the winner rescans; large r: a
+// bitonic sort.
 __global__ void __launch_bounds__(256)
 select_threshold_kernel(const float* __restrict__ sample, int n, int npad, int r, float* thr) {
   extern __shared__ float vals[];
   __shared__ float wmax[8];
   __shared__ int widx[8];
-  __shared__ float result;
   const int q = blockIdx.x;
   for (int i = threadIdx.x; i < npad; i += blockDim.x) vals[i] = (i < n) ? sample[(size_t)q * n + i] : -INFINITY;
   __syncthreads();
@@ -280,26 +280,36 @@ select_threshold_kernel(const float* __restrict__ sample, int n, int npad, int r
     return;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float best = -INFINITY;   // best of this thread's own values (indices tid, tid+256, ...)
+  int bi = -1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = vals[i];
+    if (v > best) { best = v; bi = i; }
+  }
+  float result = -INFINITY;
   for (int round = 0; round < r; ++round) {
-    float best = -INFINITY;
-    int bi = -1;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const float v = vals[i];
-      if (v > best) { best = v; bi = i; }
-    }
+    float wb = best;
+    int wi = bi;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > best || (ob == best && oi > bi)) { best = ob; bi = oi; }
+      const float ob = __shfl_xor_sync(0xffffffffu, wb, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (ob > wb || (ob == wb && oi > wi)) { wb = ob; wi = oi; }
     }
-    if (lane == 0) { wmax[warp] = best; widx[warp] = bi; }
+    if (lane == 0) { wmax[warp] = wb; widx[warp] = wi; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      float b = wmax[0]; int idx = widx[0];
-      for (int w = 1; w < 8; ++w) if (wmax[w] > b || (wmax[w] == b && widx[w] > idx)) { b = wmax[w]; idx = widx[w]; }
-      result = b;
-      if (idx >= 0) vals[idx] = -INFINITY;   // remove it for the next round
+    float b = wmax[0];
+    int idx = widx[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) if (wmax[w] > b || (wmax[w] == b && widx[w] > idx)) { b = wmax[w]; idx = widx[w]; }
+    result = (idx >= 0) ? b : -INFINITY;
+    if (idx >= 0 && idx == bi) {             // this thread owns the winner: drop it and rescan its values
+      vals[idx] = -INFINITY;
+      best = -INFINITY; bi = -1;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = vals[i];
+        if (v > best) { best = v; bi = i; }
+      }
     }
     __syncthreads();
   }
@@ -385,7 +395,8 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
     // r' = rank (within the sample) of the score that ~T rows of the whole catalog reach
     const double rp = (double)T * (double)ns_rows / (double)N;
     const double nvals = (double)(slots * (BLOCK_N / 32));
-    if (rp < 11.5 || rp > 0.7 * nvals) return false;
+    if (rp < 11.5 || rp > 1.5 * nvals) return false;
+    if (nvals < 128.0 && stride > 1) return false;   // too few chunk maxima for a stable quantile: sample denser
     // The top-r' sampled rows occupy about nvals*(1-exp(-r'/nvals)) distinct 32-row chunks, so that is
     // the rank to read among the chunk maxima (a smaller rank would only over-fetch; never unsafe).
     const double r = nvals * (1.0 - exp(-rp / nvals));
@@ -398,23 +409,19 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   bool reliable = false;
   const int Tmax = FINALIZE_MAX_CAND / 4;
   {
-    int T = 4 * K < 128 ? 128 : 4 * K;
+    int T = 6 * K < 256 ? 256 : 6 * K;   // extra candidates are cheap (finalize prunes before rescoring)
     if (T > Tmax) T = Tmax;
-    // (a) the usual case: r ~ 16 from a sparse sample
-    reliable = try_plan(T, T / 16);
-    // (b) huge catalogs: the slot cap forces a sparser sample; raise T so that r stays >= 12
-    if (!reliable && (pl.num_tiles + (T / 16 > 0 ? T / 16 : 1) - 1) / (T / 16 > 0 ? T / 16 : 1) > SAMPLE_MAX_SLOTS) {
+    // (a) r' ~ 16 from a sparse sample; small catalogs / large K fall through to denser samples
+    for (int stride = T / 16; !reliable && stride >= 1; stride /= 2) reliable = try_plan(T, stride);
+    // (b) huge catalogs: the slot cap forces a sparser sample; raise T so that r' stays >= 12
+    if (!reliable && (pl.num_tiles + T / 16 - 1) / (T / 16) > SAMPLE_MAX_SLOTS) {
       const int stride = (pl.num_tiles + SAMPLE_MAX_SLOTS - 1) / SAMPLE_MAX_SLOTS;
       for (int T2 = T; T2 <= Tmax && !reliable; T2 += T2 / 4 + 1) reliable = try_plan(T2, stride);
     }
-    // (c) small catalogs / large K: denser samples, down to every tile, and a leaner budget
-    const int T_lean = (2 * K + 64 < 128) ? 128 : 2 * K + 64;
-    for (int stride = T / 32; !reliable && stride >= 1; stride /= 2) reliable = try_plan(T, stride);
+    // (c) K is a large fraction of N: a leaner budget
+    const int T_lean = (3 * K + 64 < 128) ? 128 : 3 * K + 64;
     if (!reliable && T_lean < T && T_lean <= Tmax)
-      for (int stride = T_lean / 16; !reliable; stride /= 2) {
-        reliable = try_plan(T_lean, stride);
-        if (stride <= 1) break;
-      }
+      for (int stride = T_lean / 16; !reliable && stride >= 1; stride /= 2) reliable = try_plan(T_lean, stride);
   }
   int C = 4096;
   if (reliable) while (C < 4 * pl.target) C <<= 1;

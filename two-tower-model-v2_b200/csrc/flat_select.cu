@@ -53,7 +53,15 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ qs, const fl
 }
 
 // ------------------------------------------------------------------------------------------
-// finalize: one CTA per query
+// finalize: one CTA per query.
+//   1. sort the candidate list by its bf16 tensor-core score;
+//   2. prune: with b_K the K-th largest bf16 score, only rows with bf16 score >= b_K - 2*eps can
+//      belong to the fp32 top-K (K rows have fp32 >= b_K - eps, and a row's fp32 score is below its
+//      bf16 score + eps), so only those are rescored (about K + a few dozen 1.5 KB row gathers
+//      instead of the whole over-fetched list);
+//   3. rescore the survivors in fp32 against the fp32 table, sort by (score desc, row asc), emit K;
+//   4. certificate: the prune cutoff must not fall below the scan threshold, otherwise a row the
+//      scan never reported could qualify -> flag the query for the exact path.
 __global__ void __launch_bounds__(512)
 flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn, long long N, int D, int K,
                      long long id_offset, const float* __restrict__ thr, const float* __restrict__ eps,
@@ -62,30 +70,54 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
                      int* __restrict__ n_uncertified) {
   extern __shared__ __align__(16) unsigned char fsm[];
   unsigned long long* key = reinterpret_cast<unsigned long long*>(fsm);
+  __shared__ int s_m;
   const int q = blockIdx.x;
   const unsigned int n_raw = cand_cnt[q];
   const bool overflow = n_raw > (unsigned int)cand_cap;
   const int n = overflow ? cand_cap : (int)n_raw;
   const int P = next_pow2(n < 2 ? 2 : n);   // >= 2 keeps qs 16-byte aligned
   float* qs = reinterpret_cast<float*>(key + P);
+  const float my_eps = eps[q];
+  const float t = thr[q];
+  const uint2* mine = cand + (size_t)q * cand_cap;
   for (int d = threadIdx.x; d < D; d += blockDim.x) qs[d] = qn[(long long)q * D + d];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    unsigned long long kk = 0ull;
+    if (i < n) { const uint2 c = mine[i]; kk = make_key(__uint_as_float(c.x), c.y); }
+    key[i] = kk;
+  }
+  if (threadIdx.x == 0) s_m = n;
   __syncthreads();
+  bitonic_sort_desc(key, P);
 
+  // ---- prune by bf16 score -----------------------------------------------------------------
+  float cutoff = -INFINITY;
+  if (n >= K) cutoff = key_score(key[K - 1]) - 2.f * my_eps;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const bool in = key_score(key[i]) >= cutoff;
+    const bool next_in = (i + 1 < n) && (key_score(key[i + 1]) >= cutoff);
+    if (in && !next_in) s_m = i + 1;         // sorted: exactly one boundary
+  }
+  __syncthreads();
+  const int m = s_m;
+
+  // ---- fp32 rescoring of the m survivors (in place) -------------------------------------------
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(Xn) & 15) == 0);
-  const uint2* mine = cand + (size_t)q * cand_cap;
-  const float my_eps = eps[q];
   int bad = 0;   // self-check: a candidate's tensor-core score must match its fp32 rescoring within eps
   constexpr int U = 4;   // candidates rescored concurrently per warp (independent loads in flight)
-  for (int i0 = warp * U; i0 < n; i0 += nwarps * U) {
-    uint2 c[U];
+  for (int i0 = warp * U; i0 < m; i0 += nwarps * U) {
+    uint32_t row[U];
+    float bsc[U];
     bool ok[U];
     float a[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int i = i0 + u;
-      c[u] = (i < n) ? mine[i] : make_uint2(0u, 0xffffffffu);
-      ok[u] = (i < n) && ((long long)c[u].y < N);   // row >= N cannot happen unless the scan is broken
+      const unsigned long long kk = (i < m) ? key[i] : 0ull;
+      row[u] = key_row(kk);
+      bsc[u] = key_score(kk);
+      ok[u] = (i < m) && ((long long)row[u] < N);   // row >= N cannot happen unless the scan is broken
       a[u] = 0.f;
     }
     if (vec) {
@@ -95,7 +127,7 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
         float4 x[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          x[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(Xn + (long long)c[u].y * D) + cc)
+          x[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(Xn + (long long)row[u] * D) + cc)
                        : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -108,17 +140,18 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
         const float y = qs[d];
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          if (ok[u]) a[u] = fmaf(__ldg(Xn + (long long)c[u].y * D + d), y, a[u]);
+          if (ok[u]) a[u] = fmaf(__ldg(Xn + (long long)row[u] * D + d), y, a[u]);
       }
     }
+    __syncwarp();
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const float sc = warp_sum(a[u]);
       const int i = i0 + u;
-      if (lane == 0 && i < n) {
+      if (lane == 0 && i < m) {
         if (ok[u]) {
-          key[i] = make_key(sc, c[u].y);
-          if (!(fabsf(__uint_as_float(c[u].x) - sc) <= my_eps)) bad = 1;
+          key[i] = make_key(sc, row[u]);
+          if (!(fabsf(bsc[u] - sc) <= my_eps)) bad = 1;
         } else {
           key[i] = 0ull;
           bad = 1;
@@ -126,12 +159,14 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
       }
     }
   }
-  for (int i = n + threadIdx.x; i < P; i += blockDim.x) key[i] = 0ull;
+  const int P2 = next_pow2(m < 2 ? 2 : m);
   const int any_bad = __syncthreads_or(bad);
-  bitonic_sort_desc(key, P);
+  for (int i = m + threadIdx.x; i < P2; i += blockDim.x) key[i] = 0ull;
+  __syncthreads();
+  bitonic_sort_desc(key, P2);
 
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
-    if (i < n) {
+    if (i < m) {
       scores[(long long)q * K + i] = key_score(key[i]);
       ids[(long long)q * K + i] = (long long)key_row(key[i]) + id_offset;
     } else {
@@ -140,12 +175,9 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
     }
   }
   if (threadIdx.x == 0) {
-    // Certificate.  Rows outside the candidate list have a bf16 tensor-core score < thr, hence an
-    // fp32 score < thr + eps.  If the K-th best rescored candidate reaches thr + eps, none of them
-    // can enter (or tie into) the top-K.
-    const float t = thr[q];
+    // Rows the scan did not report have a bf16 score < thr; they are harmless iff thr <= cutoff.
     bool ok = !overflow && n >= K && !any_bad;
-    if (ok && !(t == -INFINITY)) ok = key_score(key[K - 1]) >= t + my_eps;
+    if (ok && !(t == -INFINITY)) ok = cutoff >= t;
     flags[q] = ok ? 1 : 0;
     if (!ok) atomicAdd(n_uncertified, 1);
   }
