@@ -155,9 +155,10 @@ int64_t tt_kernel_launch_count(void);
 int tt_profile_scan_arm(int max_records);
 int tt_profile_scan_read(float* ms_out, int max_out);
 
-/* Host-only: the planner's decisions for (N, D, nq, K) as 16 ints: supported, block_m, k_blocks,
- * stages, query_blocks, tiles, use_threshold, route_exact, target_candidates, candidate_capacity,
- * sample_stride, sample_slots, sample_rank, main_slices, sample_slices, smem_bytes. */
+/* Host-only: the planner's decisions for (N, D, nq, K) as 16 ints: supported, queries per unit (64 /
+ * 128 single CTA, 256 CTA pair), k_blocks, stages, query_units, tiles, use_threshold, route_exact,
+ * target_candidates, candidate_capacity, sample_stride, sample_slots, sample_rank, main_slices,
+ * segment_capacity, smem_bytes. */
 int tt_flat_plan_describe(int64_t N, int D, int nq, int K, int32_t* out16);
 
 /* Diagnostic / parity-test entry: the raw bf16 tensor-core scores of EVERY row of a small catalog

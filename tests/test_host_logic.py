@@ -95,8 +95,8 @@ def _plan(N, D, nq, K):
     from two_tower_model_v2_b200 import _native
     out = (ctypes.c_int32 * 16)()
     _native.check(_native.load().tt_flat_plan_describe(N, D, nq, K, out), "tt_flat_plan_describe")
-    names = ("supported block_m k_blocks stages query_blocks tiles use_threshold route_exact target cap "
-             "stride slots rank main_slices sample_slices smem").split()
+    names = ("supported unit_queries k_blocks stages query_units tiles use_threshold route_exact target cap "
+             "stride slots rank main_slices seg_cap smem").split()
     return dict(zip(names, out))
 
 
@@ -104,18 +104,25 @@ def test_search_planner_invariants():
     """The host-side planner (no GPU needed): smem budget, tiling and candidate-budget routing."""
     for N, D, nq, K in [(10_000_000, 384, 128, 100), (1_000_000, 384, 4096, 100), (100_000_000, 384, 1, 100),
                         (10_000_000, 768, 64, 100), (20_000, 384, 2000, 10), (9_000, 64, 16, 1000),
-                        (70_000, 256, 40, 500), (2_049, 32, 9, 100), (1, 8, 1, 1), (12_500_000, 384, 1024, 1000)]:
+                        (70_000, 256, 40, 500), (2_049, 32, 9, 100), (1, 8, 1, 1), (12_500_000, 384, 1024, 1000),
+                        (10_000_000, 384, 129, 100), (10_000_000, 768, 300, 100)]:
         p = _plan(N, D, nq, K)
         assert p["supported"] == 1 and p["smem"] <= 227 * 1024 and p["stages"] >= 2
-        assert p["block_m"] == (128 if D <= 512 else 64)
+        # CTA pairs (256 queries per unit) exactly when nq > 128 and the 128-query operand fits (D <= 512)
+        want = 64 if D > 512 else (256 if nq > 128 else 128)
+        assert p["unit_queries"] == want
         assert p["k_blocks"] == -(-D // 64) and p["tiles"] == -(-N // 256)
-        assert p["query_blocks"] == -(-nq // p["block_m"])
-        assert 1 <= p["main_slices"] <= p["tiles"] and p["main_slices"] * p["query_blocks"] <= max(148, p["query_blocks"])
+        assert p["query_units"] == -(-nq // want)
+        assert 1 <= p["main_slices"] <= max(1, p["tiles"])
         assert not (p["use_threshold"] and p["route_exact"])
         if p["use_threshold"]:
-            assert p["target"] >= 2 * K and p["cap"] >= 4 * p["target"] or p["cap"] == 16384
+            assert p["target"] >= 2 * K and (p["cap"] >= 4 * p["target"] or p["cap"] == 16384)
             assert 1 <= p["rank"] <= p["slots"] * 8 and p["slots"] <= 4096
+            assert p["seg_cap"] >= min(512, -(-p["tiles"] // p["main_slices"]) * 256)
         elif not p["route_exact"]:
-            assert p["cap"] >= N            # every row is a candidate and must fit the list
+            assert p["cap"] >= N and p["seg_cap"] * p["main_slices"] >= N   # every row is a candidate and must fit
     assert _plan(10_000_000, 384, 128, 100)["use_threshold"] == 1
     assert _plan(9_000, 64, 16, 1000)["use_threshold"] == 0
+    # units fill the machine: one unit per SM (single) / SM pair (pair) on a 148-SM part
+    assert _plan(10_000_000, 384, 128, 100)["main_slices"] == 148
+    assert _plan(10_000_000, 384, 256, 100)["main_slices"] == 74

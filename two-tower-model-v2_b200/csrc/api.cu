@@ -32,8 +32,8 @@ static SearchWs search_ws_layout(const ScanPlan& pl, int D, int nq) {
   w.qh = o;     o += align_up((size_t)pl.nq_pad * pl.Dp * 2, 256);
   w.eps = o;    o += align_up((size_t)nq * sizeof(float), 256);
   w.thr = o;    o += align_up((size_t)nq * sizeof(float), 256);
-  w.cnt = o;    o += align_up((size_t)nq * sizeof(unsigned int), 256);
-  w.cand = o;   o += align_up((size_t)nq * pl.cand_cap * 8, 256);
+  w.cnt = o;    o += align_up((size_t)nq * pl.main_slices * sizeof(unsigned int), 256);
+  w.cand = o;   o += align_up((size_t)nq * pl.main_slices * pl.seg_cap * 8, 256);
   w.sample = o; o += align_up((size_t)pl.sample_slots * 8 * pl.nq_pad * sizeof(float), 256);
   w.total = o;
   return w;
@@ -121,7 +121,6 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_search(const float
   void* cand = ws + w.cand;
   float* sample = reinterpret_cast<float*>(ws + w.sample);
 
-  TT_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(unsigned int), st));
   if (int e = launch_prep_queries(q, nq, pl.nq_pad, D, pl.Dp, stats, qn, qh, eps, st)) return e;
   if (int e = launch_scan(pl, qh, Xh, N, nq, thr, cnt, cand, sample, st)) return e;
   return launch_finalize(pl, qn, Xn, N, D, nq, K, id_offset, thr, eps, cnt, cand, scores,
@@ -131,13 +130,16 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_search(const float
 // ------------------------------------------------------------------------------------------
 // Diagnostic: dense bf16 tensor-core scores of a small catalog (parity tests of the scan itself).
 namespace tt {
-__global__ void scatter_scores_kernel(const unsigned int* __restrict__ cnt, const uint2* __restrict__ cand,
-                                      int cap, long long N, float* __restrict__ out) {
+__global__ void scatter_scores_kernel(const unsigned int* __restrict__ seg_cnt, const uint2* __restrict__ cand,
+                                      int nslices, int seg_cap, long long N, float* __restrict__ out) {
   const int q = blockIdx.y;
-  const unsigned int n = min(cnt[q], (unsigned int)cap);
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint2 c = cand[(size_t)q * cap + i];
-    if ((long long)c.y < N) out[(long long)q * N + c.y] = __uint_as_float(c.x);
+  for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+    const unsigned int n = min(seg_cnt[(size_t)q * nslices + sl], (unsigned int)seg_cap);
+    const uint2* seg = cand + ((size_t)q * nslices + sl) * seg_cap;
+    for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint2 c = seg[i];
+      if ((long long)c.y < N) out[(long long)q * N + c.y] = __uint_as_float(c.x);
+    }
   }
 }
 }  // namespace tt
@@ -147,7 +149,7 @@ extern "C" __attribute__((visibility("default"))) size_t tt_flat_scan_scores_wor
   ScanPlan pl = make_scan_plan(N, D, nq, 1);
   pl.use_threshold = false;
   pl.route_exact = false;
-  pl.cand_cap = (int)N;
+  pl.seg_cap = (pl.num_tiles + pl.main_slices - 1) / pl.main_slices * 256;
   return search_ws_layout(pl, D, nq).total;
 }
 
@@ -160,7 +162,7 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_scan_scores(const 
   if (!pl.supported) { set_error("tt_flat_scan_scores: D too large"); return TT_ERR_UNSUPPORTED; }
   pl.use_threshold = false;
   pl.route_exact = false;
-  pl.cand_cap = (int)N;
+  pl.seg_cap = (pl.num_tiles + pl.main_slices - 1) / pl.main_slices * 256;
   const SearchWs w = search_ws_layout(pl, D, nq);
   if (workspace_bytes < w.total) { set_error("tt_flat_scan_scores: workspace too small"); return TT_ERR_WORKSPACE; }
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
@@ -171,11 +173,10 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_scan_scores(const 
   unsigned int* cnt = reinterpret_cast<unsigned int*>(ws + w.cnt);
   void* cand = ws + w.cand;
   float* sample = reinterpret_cast<float*>(ws + w.sample);
-  TT_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(unsigned int), st));
   TT_CHECK_CUDA(cudaMemsetAsync(out, 0xFF, (size_t)nq * N * sizeof(float), st));   // NaN = "row never reported"
   if (int e = launch_prep_queries(q, nq, pl.nq_pad, D, pl.Dp, stats, qn, qh, eps, st)) return e;
   if (int e = launch_scan(pl, qh, Xh, N, nq, thr, cnt, cand, sample, st)) return e;
-  scatter_scores_kernel<<<dim3(64, nq), 256, 0, st>>>(cnt, reinterpret_cast<const uint2*>(cand), pl.cand_cap, N, out);
+  scatter_scores_kernel<<<dim3(64, nq), 256, 0, st>>>(cnt, reinterpret_cast<const uint2*>(cand), pl.main_slices, pl.seg_cap, N, out);
   TT_CHECK_LAUNCH();
   return TT_OK;
 }
@@ -184,9 +185,9 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_scan_scores(const 
 extern "C" __attribute__((visibility("default"))) int tt_flat_plan_describe(int64_t N, int D, int nq, int K, int32_t* out16) {
   TT_CHECK_ARG(out16 != nullptr && N >= 1 && D >= 1 && nq >= 1 && K >= 1, "bad argument");
   const ScanPlan pl = make_scan_plan(N, D, nq, K);
-  const int32_t v[16] = {pl.supported, pl.block_m, pl.num_kb, pl.num_stages, pl.nqb, pl.num_tiles, pl.use_threshold,
-                         pl.route_exact, pl.target, pl.cand_cap, pl.sample_stride, pl.sample_slots, pl.sample_rank,
-                         pl.main_slices, pl.sample_slices, (int32_t)pl.smem_bytes};
+  const int32_t v[16] = {pl.supported, pl.pair ? 2 * pl.block_m : pl.block_m, pl.num_kb, pl.num_stages, pl.nqu, pl.num_tiles,
+                         pl.use_threshold, pl.route_exact, pl.target, pl.cand_cap, pl.sample_stride, pl.sample_slots,
+                         pl.sample_rank, pl.main_slices, pl.seg_cap, (int32_t)pl.smem_bytes};
   for (int i = 0; i < 16; ++i) out16[i] = v[i];
   return TT_OK;
 }

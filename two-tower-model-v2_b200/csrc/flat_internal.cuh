@@ -7,16 +7,20 @@
 namespace tt {
 
 constexpr int SAMPLE_MAX_SLOTS = 4096;      // sampled tiles per query (8 chunk maxima each are staged in smem)
+constexpr int FINALIZE_MAX_SLICES = 1024;   // catalog slices per query the finalize kernel gathers
 constexpr int FINALIZE_MAX_CAND = 16384;   // candidates per query the finalize kernel can sort (128 KiB smem)
 
 // Everything the host decides about one search call (pure function of N, D, nq, K and the SM count).
 struct ScanPlan {
   int Dp, num_kb, block_m, num_stages;
   bool supported;
+  bool pair;           // 2-CTA clusters running cta_group::2 MMAs (nq > 128)
   size_t smem_bytes;
   int nqb, nq_pad, num_tiles;
+  int nqu;             // query units the grid is built from: query blocks, or pairs of them
   int target;          // expected candidates per query
-  int cand_cap;        // capacity of a query's candidate list
+  int cand_cap;        // candidates of one query the finalize kernel sorts (sum over slices)
+  int seg_cap;         // capacity of one (query, slice) candidate segment
   bool use_threshold;  // false: every row is a candidate (small catalogs)
   bool route_exact;    // true: K is too large a fraction of N for a sampled threshold -> fp32 exact path
   int main_slices;
@@ -30,11 +34,11 @@ int launch_prep_queries(const float* q, int nq, int nq_pad, int D, int Dp, const
 
 // sample pass (if plan.use_threshold) + threshold selection + main scan
 int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq,
-                float* thr, unsigned int* cand_cnt, void* cand, float* sample_buf, cudaStream_t st);
+                float* thr, unsigned int* seg_cnt, void* cand, float* sample_buf, cudaStream_t st);
 
 // fp32 rescoring of every candidate, exact sort, certificate
 int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long long N, int D, int nq, int K,
-                    long long id_offset, const float* thr, const float* eps, const unsigned int* cand_cnt,
+                    long long id_offset, const float* thr, const float* eps, const unsigned int* seg_cnt,
                     const void* cand, float* scores, long long* ids, int* flags, int* n_uncertified,
                     cudaStream_t st);
 

@@ -2,24 +2,32 @@
 // faiss.IndexFlatIP.search as called at src/inference/vector_db.py:160,197).
 //
 // scores[q, r] = <qh[q,:], Xh[r,:]>  (bf16 operands, fp32 accumulation in TMEM) for one block of
-// BLOCK_M queries against a stream of 256-row catalog tiles.  The score matrix never reaches
-// shared or global memory: epilogue warps read the accumulator straight out of TMEM and keep
-// only rows whose score reaches the query's threshold, appending (score, row) to a small
-// per-query candidate list in global memory (a few hundred entries for the whole catalog).
+// queries against a stream of 256-row catalog tiles.  The score matrix never reaches shared or
+// global memory: epilogue warps read the accumulator straight out of TMEM and keep only rows whose
+// score reaches the query's threshold, appending (score, row) to a small candidate segment that
+// belongs to this (query, catalog slice) alone - a register counter, no atomics.
 //
 // CTA anatomy (256 threads, 1 CTA / SM):
-//   warp 0  lane 0 : TMA producer   - query block once (resident A operand, 128B swizzle),
-//                                     then catalog K-blocks [256 rows x 64 bf16] through a
-//                                     num_stages-deep mbarrier ring
-//   warp 1  lane 0 : MMA issuer     - tcgen05.mma cta_group::1 kind::f16, M=BLOCK_M, N=256, K=16;
-//                                     accumulators double-buffered in TMEM (2 x 256 columns)
+//   warp 0  lane 0 : TMA producer   - query block once (resident A operand, 128B swizzle), then
+//                                     catalog K-blocks [rows x 64 bf16] through an mbarrier ring
+//   warp 1  lane 0 : MMA issuer     - tcgen05.mma kind::f16, N = 256, K = 16; accumulators
+//                                     double-buffered in TMEM (2 x 256 fp32 columns)
 //   warp 2         : TMEM allocator
 //   warps 4-7      : epilogue       - tcgen05.ld 32x32b, one query per thread, threshold in a
 //                                     register; overlaps the next tile's MMAs
 //
-// Work decomposition: unit u = blockIdx.x -> (query block u % nqb, catalog slice u / nqb), so
-// that concurrently resident CTAs share catalog tiles through L2 when there are several query
-// blocks.
+// Two tilings:
+//   single (nq <= 128, or D > 512): cta_group::1, M = BLOCK_M queries (128, or 64 when D > 512).
+//       HBM-bound regime: every CTA streams its own slice of the catalog once.
+//   pair   (nq > 128): a cluster of two CTAs runs cta_group::2 MMAs with M = 256 queries (128 per
+//       CTA, each resident in its own shared memory) and each CTA loads only HALF of every catalog
+//       tile (128 rows): per-SM shared-memory traffic (operand reads + TMA writes) drops from
+//       ~160 to ~96 bytes/cycle, which is what lets the tensor pipe run near its rate, and L2->SM
+//       traffic halves.
+//
+// Work decomposition: unit = (query block [pair], catalog slice); slices interleave tiles
+// (tile = slice + t * nslices) so that contiguous clusters of similar catalog rows spread over all
+// slices, and units that share a slice run next to each other and share catalog tiles through L2.
 //
 // Two epilogue modes:
 //   SAMPLE : scan every `tile_stride`-th tile and write only the maximum score of each 32-row
@@ -41,35 +49,50 @@ constexpr int SCAN_THREADS = 256;
 constexpr int BLOCK_N = 256;                    // catalog rows per tile
 constexpr int BLOCK_K = 64;                     // bf16 per K-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KiB
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;                  // 2 accumulator buffers x 256 fp32 columns
+constexpr int CHUNKS = BLOCK_N / 32;
 
 struct ScanParams {
   long long N;            // catalog rows
   int nq;                 // valid queries
   int num_kb;             // K-blocks per row (Dp / 64)
   int num_stages;         // B ring depth
-  int nqb;                // query blocks
+  int nqu;                // query units (query blocks, or query-block pairs)
+  int nslices;            // catalog slices
   int num_slots;          // tiles to visit in total (main: all tiles; sample: sampled tiles)
   int tile_stride;        // tile index = slot * tile_stride
   // MAIN
   const float* thr;       // [nq]
-  unsigned int* cand_cnt; // [nq]
-  uint2* cand;            // [nq, cand_cap]  (score bits, row)
-  int cand_cap;
+  unsigned int* seg_cnt;  // [nq, nslices]
+  uint2* cand;            // [nq, nslices, seg_cap]  (score bits, row)
+  int seg_cap;
   // SAMPLE
   float* sample_out;      // [nq_pad, num_slots, 8] maxima of the 32-row chunks of every sampled tile
-  int nq_pad;
 };
 
-template <int BLOCK_M, bool SAMPLE>
+__device__ __forceinline__ float max_tree(const uint32_t (&v)[32]) {
+  float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+#pragma unroll
+  for (int j = 4; j < 32; j += 4) {
+    m0 = fmaxf(m0, __uint_as_float(v[j]));
+    m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+    m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+    m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+template <int BLOCK_M, bool SAMPLE, bool PAIR>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                  const ScanParams p) {
   constexpr int A_KB_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;            // rows of a tile this CTA loads
+  constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
+  constexpr int UMMA_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
   extern __shared__ uint8_t smem_raw[];
-  // 128B-swizzled operand tiles need 1024-byte alignment
+  // 128B-swizzled operand tiles need 1024-byte alignment (identical offsets in both CTAs of a pair)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + (size_t)p.num_kb * A_KB_BYTES;
@@ -83,15 +106,15 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   // ---- work assignment ----------------------------------------------------------------------
-  const int unit = blockIdx.x;
-  const int qb = unit % p.nqb;
-  const int slice = unit / p.nqb;
-  const int nslices = gridDim.x / p.nqb;
-  const int slot_begin = (int)(((long long)p.num_slots * slice) / nslices);
-  const int slot_end = (int)(((long long)p.num_slots * (slice + 1)) / nslices);
-  const int ntiles = slot_end - slot_begin;
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int qu = unit % p.nqu;
+  const int slice = unit / p.nqu;
+  const int qb = PAIR ? (2 * qu + (int)cta_rank) : qu;           // 128- (or 64-) query block of this CTA
+  const int ntiles = (p.num_slots > slice) ? (p.num_slots - slice + p.nslices - 1) / p.nslices : 0;
 
   // ---- one-time setup -----------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -100,51 +123,58 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.num_stages; ++i) {
-      mbar_init(smem_u32(full_bar + i), 1);
+      mbar_init(smem_u32(full_bar + i), PAIR ? 2 : 1);     // pair: both producers arrive on the leader's barrier
       mbar_init(smem_u32(empty_bar + i), 1);
     }
-    mbar_init(smem_u32(a_full_bar), 1);
+    mbar_init(smem_u32(a_full_bar), PAIR ? 2 : 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(tmem_full_bar + i), 1);
-      mbar_init(smem_u32(tmem_empty_bar + i), 4);   // one arrival per epilogue warp
+      mbar_init(smem_u32(tmem_empty_bar + i), PAIR ? 8 : 4);   // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
+  if (PAIR) cluster_sync();        // peer barriers must be initialised before any remote arrive / 2-SM alloc
   if (warp == 2) {
-    tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_2cta(smem_u32(tmem_ptr_smem), TMEM_COLS); tmem_relinquish_2cta(); }
+    else      { tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
     // =========================== TMA producer ===============================================
     if (lane == 0) {
-      mbar_arrive_expect_tx(smem_u32(a_full_bar), (uint32_t)(p.num_kb * A_KB_BYTES));
-      for (int kb = 0; kb < p.num_kb; ++kb)
-        tma_load_2d(smem_u32(smem_a + (size_t)kb * A_KB_BYTES), &tmap_q, smem_u32(a_full_bar), kb * BLOCK_K,
-                    qb * BLOCK_M);
+      // In pair mode every TMA of either CTA signals the LEADER's barrier (the MMA issuer waits there).
+      const uint32_t a_bar = smem_u32(a_full_bar);
+      if (leader) mbar_arrive_expect_tx(a_bar, (uint32_t)(p.num_kb * A_KB_BYTES) * (PAIR ? 2u : 1u));
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        if (PAIR) tma_load_2d_2cta(smem_u32(smem_a + (size_t)kb * A_KB_BYTES), &tmap_q, a_bar, kb * BLOCK_K, qb * BLOCK_M);
+        else      tma_load_2d(smem_u32(smem_a + (size_t)kb * A_KB_BYTES), &tmap_q, a_bar, kb * BLOCK_K, qb * BLOCK_M);
+      }
+      if (PAIR && !leader) mbar_arrive_remote(a_bar, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
-        const long long tile = (long long)(slot_begin + t) * p.tile_stride;
-        const int row0 = (int)(tile * BLOCK_N);
+        const long long tile = (long long)(slice + t * p.nslices) * p.tile_stride;
+        const int row0 = (int)(tile * BLOCK_N) + (PAIR ? (int)cta_rank * B_ROWS : 0);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1, 100 + stage);
-          mbar_arrive_expect_tx(smem_u32(full_bar + stage), B_STAGE_BYTES);
-          tma_load_2d(smem_u32(smem_b + (size_t)stage * B_STAGE_BYTES), &tmap_x, smem_u32(full_bar + stage),
-                      kb * BLOCK_K, row0);
+          const uint32_t fb = smem_u32(full_bar + stage);
+          if (leader) mbar_arrive_expect_tx(fb, (uint32_t)B_STAGE_BYTES * (PAIR ? 2u : 1u));
+          if (PAIR) tma_load_2d_2cta(smem_u32(smem_b + (size_t)stage * B_STAGE_BYTES), &tmap_x, fb, kb * BLOCK_K, row0);
+          else      tma_load_2d(smem_u32(smem_b + (size_t)stage * B_STAGE_BYTES), &tmap_x, fb, kb * BLOCK_K, row0);
+          if (PAIR && !leader) mbar_arrive_remote(fb, 0);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // =========================== MMA issuer =================================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BLOCK_M, BLOCK_N);
+    // =========================== MMA issuer (leader CTA only in pair mode) ====================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(UMMA_M, BLOCK_N);
       const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem_a));
       const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem_b));
       mbar_wait(smem_u32(a_full_bar), 0, 200);
@@ -166,10 +196,17 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 bytes per K=16 step
-            mma_bf16_ss(d_tmem, a_desc + koff, b_desc + koff, idesc, (uint32_t)((kb | k) != 0));
+            if (PAIR) mma_bf16_ss_2cta(d_tmem, a_desc + koff, b_desc + koff, idesc, (uint32_t)((kb | k) != 0));
+            else      mma_bf16_ss(d_tmem, a_desc + koff, b_desc + koff, idesc, (uint32_t)((kb | k) != 0));
           }
-          mma_commit(smem_u32(empty_bar + stage));          // smem slot free once these MMAs retire
-          if (kb == p.num_kb - 1) mma_commit(smem_u32(tmem_full_bar + buf));
+          // smem slot free (in both CTAs) once these MMAs retire; accumulator ready after the last K-block
+          if (PAIR) {
+            mma_commit_2cta(smem_u32(empty_bar + stage));
+            if (kb == p.num_kb - 1) mma_commit_2cta(smem_u32(tmem_full_bar + buf));
+          } else {
+            mma_commit(smem_u32(empty_bar + stage));
+            if (kb == p.num_kb - 1) mma_commit(smem_u32(tmem_full_bar + buf));
+          }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -186,66 +223,106 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     float thr = INFINITY;
     if (!SAMPLE && valid) thr = __ldg(p.thr + q);
-    unsigned int* my_cnt = SAMPLE ? nullptr : (p.cand_cnt + (valid ? q : 0));
-    uint2* my_cand = SAMPLE ? nullptr : (p.cand + (size_t)(valid ? q : 0) * p.cand_cap);
+    uint2* my_cand = SAMPLE ? nullptr : (p.cand + ((size_t)(valid ? q : 0) * p.nslices + slice) * p.seg_cap);
+    unsigned int my_cnt = 0;
 
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const uint32_t use_phase = (uint32_t)(t >> 1) & 1u;
-      const long long tile = (long long)(slot_begin + t) * p.tile_stride;
-      const long long row0 = tile * BLOCK_N;
+      const int slot = slice + t * p.nslices;
+      const long long row0 = (long long)slot * p.tile_stride * BLOCK_N;
       const int ncols = (int)min((long long)BLOCK_N, p.N - row0);   // last tile may be partial
       mbar_wait(smem_u32(tmem_full_bar + buf), use_phase, 300 + buf);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BLOCK_N);
-      float cmax[BLOCK_N / 32];   // SAMPLE: maximum of each 32-row chunk of this tile
+      float cmax[CHUNKS];   // SAMPLE: maximum of each 32-row chunk of this tile
 #pragma unroll
-      for (int c = 0; c < BLOCK_N / 32; ++c) cmax[c] = -INFINITY;
+      for (int c = 0; c < CHUNKS; ++c) cmax[c] = -INFINITY;
+
+      if (ncols == BLOCK_N) {
+        // ---- full tile: two 32-column chunks in flight per wait ---------------------------------
 #pragma unroll
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        if (c * 32 >= ncols) continue;                 // warp-uniform (partial last tile)
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
-        const int limit = ncols - c * 32;              // >= 1; columns >= limit are padding rows
-        float m = -INFINITY;
+        for (int c = 0; c < CHUNKS; c += 2) {
+          uint32_t v0[32], v1[32];
+          __syncwarp();
+          tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v0);
+          tmem_ld_32x32(taddr0 + (uint32_t)(c * 32 + 32), v1);
+          tmem_ld_wait();
+          const float m0 = max_tree(v0);
+          const float m1 = max_tree(v1);
+          if (SAMPLE) {
+            cmax[c] = m0; cmax[c + 1] = m1;
+          } else {
+            if (fmaxf(m0, m1) >= thr) {                    // rare: some column of these chunks qualifies
+              const uint32_t rbase = (uint32_t)row0 + (uint32_t)(c * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) m = fmaxf(m, (j < limit) ? __uint_as_float(v[j]) : -INFINITY);
-        if (SAMPLE) {
-          cmax[c] = m;
-        } else {
-          if (m >= thr) {                              // rare: some column of this chunk qualifies
+              for (int j = 0; j < 32; ++j) {
+                if (__uint_as_float(v0[j]) >= thr) {
+                  if (my_cnt < (unsigned int)p.seg_cap) my_cand[my_cnt] = make_uint2(v0[j], rbase + (uint32_t)j);
+                  ++my_cnt;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (__uint_as_float(v1[j]) >= thr) {
+                  if (my_cnt < (unsigned int)p.seg_cap) my_cand[my_cnt] = make_uint2(v1[j], rbase + 32u + (uint32_t)j);
+                  ++my_cnt;
+                }
+              }
+            }
+          }
+        }
+      } else {
+        // ---- partial last tile: columns >= ncols are zero-filled padding rows --------------------
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; ++c) {
+          if (c * 32 >= ncols) break;                      // warp-uniform
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          const int limit = ncols - c * 32;
+          float m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, (j < limit) ? __uint_as_float(v[j]) : -INFINITY);
+          if (SAMPLE) {
+#pragma unroll
+            for (int cc = 0; cc < CHUNKS; ++cc) if (cc == c) cmax[cc] = m;
+          } else if (m >= thr) {
             const uint32_t rbase = (uint32_t)row0 + (uint32_t)(c * 32);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(v[j]);
-              if (j < limit && s >= thr) {
-                const unsigned int pos = atomicAdd(my_cnt, 1u);
-                if (pos < (unsigned int)p.cand_cap) my_cand[pos] = make_uint2(v[j], rbase + (uint32_t)j);
+              if (j < limit && __uint_as_float(v[j]) >= thr) {
+                if (my_cnt < (unsigned int)p.seg_cap) my_cand[my_cnt] = make_uint2(v[j], rbase + (uint32_t)j);
+                ++my_cnt;
               }
             }
           }
         }
       }
-      // release this accumulator buffer to the MMA warp
+      // release this accumulator buffer to the MMA issuer (on the leader CTA)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tmem_empty_bar + buf));
+      if (lane == 0) {
+        if (PAIR && !leader) mbar_arrive_remote(smem_u32(tmem_empty_bar + buf), 0);
+        else mbar_arrive(smem_u32(tmem_empty_bar + buf));
+      }
       if (SAMPLE && valid) {
-        float4* o = reinterpret_cast<float4*>(p.sample_out + ((size_t)q * p.num_slots + (slot_begin + t)) * (BLOCK_N / 32));
+        float4* o = reinterpret_cast<float4*>(p.sample_out + ((size_t)q * p.num_slots + slot) * CHUNKS);
         o[0] = make_float4(cmax[0], cmax[1], cmax[2], cmax[3]);
         o[1] = make_float4(cmax[4], cmax[5], cmax[6], cmax[7]);
       }
     }
+    if (!SAMPLE && valid) p.seg_cnt[(size_t)q * p.nslices + slice] = my_cnt;
   }
 
   // ---- teardown ---------------------------------------------------------------------------
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -357,28 +434,47 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, int 
   return TT_OK;
 }
 
+// Number of catalog slices for `nqu` query units on `cap` concurrent units (SMs, or SM pairs):
+// the count that wastes the fewest unit slots over whole waves.
+static int pick_slices(int nqu, int cap, int max_slices) {
+  if (max_slices < 1) max_slices = 1;
+  if (nqu >= cap) return 1;
+  int best = 1;
+  double best_eff = 0.0;
+  const int hi = max_slices < 4 * cap ? max_slices : 4 * cap;
+  for (int ns = 1; ns <= hi; ++ns) {
+    const long long total = (long long)nqu * ns;
+    const long long waves = (total + cap - 1) / cap;
+    const double eff = (double)total / (double)(waves * cap);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = ns; }
+    if (total >= cap && eff > 0.97) break;     // good enough; more slices only add prologues
+  }
+  return best;
+}
+
 ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   ScanPlan pl{};
   pl.Dp = (int)tt_flat_pitch(D);
   pl.num_kb = pl.Dp / BLOCK_K;
-  // A (queries) stays resident: M=128 while it leaves room for >= 3 B stages, else M=64.
+  const int sms = num_sms();
+  // A (queries) stays resident: M=128 per CTA while it leaves room for >= 3 full-tile B stages, else M=64.
   const int budget = 227 * 1024 - 2048;   // barriers + alignment slack
   pl.block_m = 128;
-  if (budget - pl.num_kb * 128 * 128 < 3 * B_STAGE_BYTES) pl.block_m = 64;
+  if (budget - pl.num_kb * 128 * 128 < 3 * (BLOCK_N * BLOCK_K * 2)) pl.block_m = 64;
+  pl.pair = (pl.block_m == 128) && (nq > 128) && (sms >= 2);
+  const int b_stage = (pl.pair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
   const int a_bytes = pl.num_kb * pl.block_m * 128;
-  pl.num_stages = (budget - a_bytes) / B_STAGE_BYTES;
+  pl.num_stages = (budget - a_bytes) / b_stage;
   if (pl.num_stages > MAX_STAGES) pl.num_stages = MAX_STAGES;
   pl.supported = pl.num_stages >= 2;
-  pl.smem_bytes = (size_t)a_bytes + (size_t)pl.num_stages * B_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  pl.smem_bytes = (size_t)a_bytes + (size_t)pl.num_stages * b_stage + 1024 /*align*/ + 256 /*barriers*/;
   pl.nqb = (nq + pl.block_m - 1) / pl.block_m;
+  if (pl.pair) pl.nqb = (pl.nqb + 1) / 2 * 2;
   pl.nq_pad = pl.nqb * pl.block_m;
+  pl.nqu = pl.pair ? pl.nqb / 2 : pl.nqb;
   pl.num_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
-
-  const int sms = num_sms();
-  int ns = sms / pl.nqb;
-  if (ns < 1) ns = 1;
-  if (ns > pl.num_tiles) ns = pl.num_tiles;
-  pl.main_slices = ns;
+  const int cap_units = pl.pair ? sms / 2 : sms;
+  pl.main_slices = pick_slices(pl.nqu, cap_units, pl.num_tiles);
 
   // Candidate budget and sampling plan.  We aim at ~T candidates per query: the threshold is read
   // among the 32-row chunk maxima of every `stride`-th tile at the rank r' = T * n_s / N (n_s =
@@ -394,7 +490,7 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
     const long long ns_rows = last_slot * BLOCK_N + rem;
     // r' = rank (within the sample) of the score that ~T rows of the whole catalog reach
     const double rp = (double)T * (double)ns_rows / (double)N;
-    const double nvals = (double)(slots * (BLOCK_N / 32));
+    const double nvals = (double)(slots * CHUNKS);
     if (rp < 11.5 || rp > 1.5 * nvals) return false;
     if (nvals < 128.0 && stride > 1) return false;   // too few chunk maxima for a stable quantile: sample denser
     // The top-r' sampled rows occupy about nvals*(1-exp(-r'/nvals)) distinct 32-row chunks, so that is
@@ -431,51 +527,76 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   // if the catalog fits a candidate list, else the always-exact fp32 path.
   pl.route_exact = false;
   pl.use_threshold = reliable;
+  const long long slice_rows = ((long long)(pl.num_tiles + pl.main_slices - 1) / pl.main_slices) * BLOCK_N;
   if (!reliable) {
     pl.sample_stride = 1; pl.sample_slots = 1; pl.sample_rank = 1; pl.target = 0;
     if (N <= FINALIZE_MAX_CAND) {
       C = 2048;
       while (C < N) C <<= 1;
+      pl.seg_cap = (int)slice_rows;                   // a slice can report every one of its rows
     } else {
       pl.route_exact = true;
+      pl.seg_cap = 64;
     }
+  } else {
+    // Segment of one (query, slice): 4x its fair share of the target, at least 512 (bursts of
+    // near-duplicate rows land in few slices), never more than the slice has rows.
+    long long seg = 4LL * pl.target / pl.main_slices;
+    if (seg < 512) seg = 512;
+    if (seg > C) seg = C;
+    if (seg > slice_rows) seg = slice_rows;
+    pl.seg_cap = (int)((seg + 63) / 64 * 64);
   }
-  int ss = sms / pl.nqb;
-  if (ss < 1) ss = 1;
-  if (ss > pl.sample_slots) ss = pl.sample_slots;
-  pl.sample_slices = ss;
+  pl.sample_slices = pick_slices(pl.nqu, cap_units, pl.sample_slots);
   pl.cand_cap = C;
   return pl;
 }
 
-template <int BLOCK_M, bool SAMPLE>
-static int launch_scan_t(const CUtensorMap& tq, const CUtensorMap& tx, const ScanParams& sp, int grid, size_t smem,
+template <int BLOCK_M, bool SAMPLE, bool PAIR>
+static int launch_scan_t(const CUtensorMap& tq, const CUtensorMap& tx, const ScanParams& sp, int units, size_t smem,
                          cudaStream_t st) {
-  TT_CHECK_CUDA(cudaFuncSetAttribute(flat_scan_kernel<BLOCK_M, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-  flat_scan_kernel<BLOCK_M, SAMPLE><<<grid, SCAN_THREADS, smem, st>>>(tq, tx, sp);
-  TT_CHECK_LAUNCH();
+  auto kern = flat_scan_kernel<BLOCK_M, SAMPLE, PAIR>;
+  TT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(PAIR ? 2 * units : units));
+  cfg.blockDim = dim3(SCAN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch();
+  TT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tx, sp));
   return TT_OK;
 }
 
+template <bool SAMPLE>
+static int launch_scan_mode(const ScanPlan& pl, const CUtensorMap& tq, const CUtensorMap& tx, const ScanParams& sp,
+                            int units, cudaStream_t st) {
+  if (pl.pair) return launch_scan_t<128, SAMPLE, true>(tq, tx, sp, units, pl.smem_bytes, st);
+  if (pl.block_m == 128) return launch_scan_t<128, SAMPLE, false>(tq, tx, sp, units, pl.smem_bytes, st);
+  return launch_scan_t<64, SAMPLE, false>(tq, tx, sp, units, pl.smem_bytes, st);
+}
+
 int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq,
-                float* thr, unsigned int* cand_cnt, void* cand, float* sample_buf, cudaStream_t st) {
+                float* thr, unsigned int* seg_cnt, void* cand, float* sample_buf, cudaStream_t st) {
   CUtensorMap tq, tx;
   if (int e = make_tmap_bf16(&tq, qh, pl.nq_pad, pl.Dp, pl.block_m)) return e;
-  if (int e = make_tmap_bf16(&tx, Xh, N, pl.Dp, BLOCK_N)) return e;
+  if (int e = make_tmap_bf16(&tx, Xh, N, pl.Dp, pl.pair ? BLOCK_N / 2 : BLOCK_N)) return e;
 
   ScanParams sp{};
-  sp.N = N; sp.nq = nq; sp.num_kb = pl.num_kb; sp.num_stages = pl.num_stages; sp.nqb = pl.nqb;
-  sp.thr = thr; sp.cand_cnt = cand_cnt; sp.cand = reinterpret_cast<uint2*>(cand); sp.cand_cap = pl.cand_cap;
-  sp.sample_out = sample_buf; sp.nq_pad = pl.nq_pad;
+  sp.N = N; sp.nq = nq; sp.num_kb = pl.num_kb; sp.num_stages = pl.num_stages; sp.nqu = pl.nqu;
+  sp.thr = thr; sp.seg_cnt = seg_cnt; sp.cand = reinterpret_cast<uint2*>(cand); sp.seg_cap = pl.seg_cap;
+  sp.sample_out = sample_buf;
 
   if (pl.use_threshold) {
-    sp.num_slots = pl.sample_slots; sp.tile_stride = pl.sample_stride;
-    const int grid = pl.sample_slices * pl.nqb;
-    int e = (pl.block_m == 128) ? launch_scan_t<128, true>(tq, tx, sp, grid, pl.smem_bytes, st)
-                                : launch_scan_t<64, true>(tq, tx, sp, grid, pl.smem_bytes, st);
-    if (e) return e;
-    const int nvals = pl.sample_slots * (BLOCK_N / 32);
+    sp.num_slots = pl.sample_slots; sp.tile_stride = pl.sample_stride; sp.nslices = pl.sample_slices;
+    if (int e = launch_scan_mode<true>(pl, tq, tx, sp, pl.sample_slices * pl.nqu, st)) return e;
+    const int nvals = pl.sample_slots * CHUNKS;
     int npad = 1;
     while (npad < nvals) npad <<= 1;
     const size_t sm = (size_t)npad * sizeof(float);
@@ -486,11 +607,9 @@ int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N,
     fill_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thr, nq, -INFINITY);
     TT_CHECK_LAUNCH();
   }
-  sp.num_slots = pl.num_tiles; sp.tile_stride = 1;
-  const int grid = pl.main_slices * pl.nqb;
+  sp.num_slots = pl.num_tiles; sp.tile_stride = 1; sp.nslices = pl.main_slices;
   profile_scan_begin(st);
-  const int e = (pl.block_m == 128) ? launch_scan_t<128, false>(tq, tx, sp, grid, pl.smem_bytes, st)
-                                    : launch_scan_t<64, false>(tq, tx, sp, grid, pl.smem_bytes, st);
+  const int e = launch_scan_mode<false>(pl, tq, tx, sp, pl.main_slices * pl.nqu, st);
   profile_scan_end(st);
   return e;
 }

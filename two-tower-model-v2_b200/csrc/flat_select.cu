@@ -65,28 +65,45 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ qs, const fl
 __global__ void __launch_bounds__(512)
 flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn, long long N, int D, int K,
                      long long id_offset, const float* __restrict__ thr, const float* __restrict__ eps,
-                     const unsigned int* __restrict__ cand_cnt, const uint2* __restrict__ cand, int cand_cap,
+                     const unsigned int* __restrict__ seg_cnt, const uint2* __restrict__ cand, int nslices,
+                     int seg_cap, int cand_cap,
                      float* __restrict__ scores, long long* __restrict__ ids, int* __restrict__ flags,
                      int* __restrict__ n_uncertified) {
   extern __shared__ __align__(16) unsigned char fsm[];
   unsigned long long* key = reinterpret_cast<unsigned long long*>(fsm);
-  __shared__ int s_m;
+  __shared__ int s_m, s_n, s_over;
+  __shared__ int s_off[FINALIZE_MAX_SLICES + 1];
   const int q = blockIdx.x;
-  const unsigned int n_raw = cand_cnt[q];
-  const bool overflow = n_raw > (unsigned int)cand_cap;
-  const int n = overflow ? cand_cap : (int)n_raw;
+  // ---- gather this query's per-slice candidate segments -----------------------------------------
+  if (threadIdx.x == 0) {
+    int tot = 0, over = 0;
+    for (int sl = 0; sl < nslices; ++sl) {
+      unsigned int c = seg_cnt[(size_t)q * nslices + sl];
+      if (c > (unsigned int)seg_cap) { c = (unsigned int)seg_cap; over = 1; }
+      if (tot + (int)c > cand_cap) { c = (unsigned int)(cand_cap - tot); over = 1; }
+      s_off[sl] = tot;
+      tot += (int)c;
+    }
+    s_off[nslices] = tot;
+    s_n = tot; s_over = over; s_m = tot;
+  }
+  __syncthreads();
+  const bool overflow = s_over != 0;
+  const int n = s_n;
   const int P = next_pow2(n < 2 ? 2 : n);   // >= 2 keeps qs 16-byte aligned
   float* qs = reinterpret_cast<float*>(key + P);
   const float my_eps = eps[q];
   const float t = thr[q];
-  const uint2* mine = cand + (size_t)q * cand_cap;
   for (int d = threadIdx.x; d < D; d += blockDim.x) qs[d] = qn[(long long)q * D + d];
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    unsigned long long kk = 0ull;
-    if (i < n) { const uint2 c = mine[i]; kk = make_key(__uint_as_float(c.x), c.y); }
-    key[i] = kk;
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int sl = warp; sl < nslices; sl += nwarps) {
+      const int o = s_off[sl], c = s_off[sl + 1] - o;
+      const uint2* seg = cand + ((size_t)q * nslices + sl) * seg_cap;
+      for (int i = lane; i < c; i += 32) { const uint2 e = seg[i]; key[o + i] = make_key(__uint_as_float(e.x), e.y); }
+    }
+    for (int i = n + threadIdx.x; i < P; i += blockDim.x) key[i] = 0ull;
   }
-  if (threadIdx.x == 0) s_m = n;
   __syncthreads();
   bitonic_sort_desc(key, P);
 
@@ -184,14 +201,15 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
 }
 
 int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long long N, int D, int nq, int K,
-                    long long id_offset, const float* thr, const float* eps, const unsigned int* cand_cnt,
+                    long long id_offset, const float* thr, const float* eps, const unsigned int* seg_cnt,
                     const void* cand, float* scores, long long* ids, int* flags, int* n_uncertified,
                     cudaStream_t st) {
+  TT_CHECK_ARG(pl.main_slices <= FINALIZE_MAX_SLICES, "too many catalog slices");
   const size_t smem = (size_t)pl.cand_cap * 8 + (size_t)D * 4 + 16;
   TT_CHECK_CUDA(cudaFuncSetAttribute(flat_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  flat_finalize_kernel<<<nq, 512, smem, st>>>(qn, Xn, N, D, K, id_offset, thr, eps, cand_cnt,
-                                              reinterpret_cast<const uint2*>(cand), pl.cand_cap, scores, ids, flags,
-                                              n_uncertified);
+  flat_finalize_kernel<<<nq, 512, smem, st>>>(qn, Xn, N, D, K, id_offset, thr, eps, seg_cnt,
+                                              reinterpret_cast<const uint2*>(cand), pl.main_slices, pl.seg_cap,
+                                              pl.cand_cap, scores, ids, flags, n_uncertified);
   TT_CHECK_LAUNCH();
   return TT_OK;
 }
