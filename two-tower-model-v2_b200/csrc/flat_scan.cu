@@ -83,6 +83,39 @@ __device__ __forceinline__ float max_tree(const uint32_t (&v)[32]) {
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
+// Slow paths of the epilogue (warp-collective: every lane of the warp must call them).  They read
+// `ncols` consecutive accumulator columns starting at `taddr`, 8 at a time, in a rolled loop.
+__device__ __noinline__ void append_columns(uint32_t taddr, int ncols, float thr, uint32_t row_base, uint2* seg,
+                                            unsigned int& cnt, unsigned int seg_cap) {
+#pragma unroll 1
+  for (int c = 0; c < ncols; c += 8) {
+    uint32_t v[8];
+    __syncwarp();
+    tmem_ld_32x8(taddr + (uint32_t)c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (c + j < ncols && __uint_as_float(v[j]) >= thr) {
+        if (cnt < seg_cap) seg[cnt] = make_uint2(v[j], row_base + (uint32_t)(c + j));
+        ++cnt;
+      }
+    }
+  }
+}
+__device__ __noinline__ float max_columns(uint32_t taddr, int ncols) {
+  float m = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < ncols; c += 8) {
+    uint32_t v[8];
+    __syncwarp();
+    tmem_ld_32x8(taddr + (uint32_t)c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (c + j < ncols) m = fmaxf(m, __uint_as_float(v[j]));
+  }
+  return m;
+}
+
 template <int BLOCK_M, bool SAMPLE, bool PAIR>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
@@ -235,13 +268,14 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_wait(smem_u32(tmem_full_bar + buf), use_phase, 300 + buf);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BLOCK_N);
-      float cmax[CHUNKS];   // SAMPLE: maximum of each 32-row chunk of this tile
-#pragma unroll
-      for (int c = 0; c < CHUNKS; ++c) cmax[c] = -INFINITY;
+      float* sample_row = SAMPLE ? (p.sample_out + ((size_t)(valid ? q : 0) * p.num_slots + slot) * CHUNKS) : nullptr;
 
       if (ncols == BLOCK_N) {
-        // ---- full tile: two 32-column chunks in flight per wait ---------------------------------
-#pragma unroll
+        // ---- full tile.  Fast path: two 32-column chunks per TMEM wait, max-reduce, one compare.  The
+        // loop is deliberately NOT unrolled and the rare "some column qualifies" path re-reads the chunk
+        // from TMEM 8 columns at a time in a small loop: the whole epilogue stays a few hundred
+        // instructions (an unrolled 256-way compare/append thrashed the instruction cache).
+#pragma unroll 1
         for (int c = 0; c < CHUNKS; c += 2) {
           uint32_t v0[32], v1[32];
           __syncwarp();
@@ -251,53 +285,22 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const float m0 = max_tree(v0);
           const float m1 = max_tree(v1);
           if (SAMPLE) {
-            cmax[c] = m0; cmax[c + 1] = m1;
-          } else {
-            if (fmaxf(m0, m1) >= thr) {                    // rare: some column of these chunks qualifies
-              const uint32_t rbase = (uint32_t)row0 + (uint32_t)(c * 32);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (__uint_as_float(v0[j]) >= thr) {
-                  if (my_cnt < (unsigned int)p.seg_cap) my_cand[my_cnt] = make_uint2(v0[j], rbase + (uint32_t)j);
-                  ++my_cnt;
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (__uint_as_float(v1[j]) >= thr) {
-                  if (my_cnt < (unsigned int)p.seg_cap) my_cand[my_cnt] = make_uint2(v1[j], rbase + 32u + (uint32_t)j);
-                  ++my_cnt;
-                }
-              }
-            }
+            if (valid) *reinterpret_cast<float2*>(sample_row + c) = make_float2(m0, m1);
+          } else if (__any_sync(0xffffffffu, fmaxf(m0, m1) >= thr)) {   // rare
+            append_columns(taddr0 + (uint32_t)(c * 32), 64, thr, (uint32_t)row0 + (uint32_t)(c * 32), my_cand, my_cnt,
+                           (unsigned int)p.seg_cap);
           }
         }
       } else {
-        // ---- partial last tile: columns >= ncols are zero-filled padding rows --------------------
-#pragma unroll 1
-        for (int c = 0; c < CHUNKS; ++c) {
-          if (c * 32 >= ncols) break;                      // warp-uniform
-          uint32_t v[32];
-          __syncwarp();
-          tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
-          tmem_ld_wait();
-          const int limit = ncols - c * 32;
-          float m = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) m = fmaxf(m, (j < limit) ? __uint_as_float(v[j]) : -INFINITY);
-          if (SAMPLE) {
-#pragma unroll
-            for (int cc = 0; cc < CHUNKS; ++cc) if (cc == c) cmax[cc] = m;
-          } else if (m >= thr) {
-            const uint32_t rbase = (uint32_t)row0 + (uint32_t)(c * 32);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < limit && __uint_as_float(v[j]) >= thr) {
-                if (my_cnt < (unsigned int)p.seg_cap) my_cand[my_cnt] = make_uint2(v[j], rbase + (uint32_t)j);
-                ++my_cnt;
-              }
-            }
+        // ---- partial last tile: columns >= ncols are zero-filled padding rows ----------------------
+        if (SAMPLE) {
+          for (int c = 0; c < CHUNKS; ++c) {
+            const int limit = min(32, ncols - c * 32);
+            const float m = (limit > 0) ? max_columns(taddr0 + (uint32_t)(c * 32), limit) : -INFINITY;
+            if (valid) sample_row[c] = m;
           }
+        } else {
+          append_columns(taddr0, ncols, thr, (uint32_t)row0, my_cand, my_cnt, (unsigned int)p.seg_cap);
         }
       }
       // release this accumulator buffer to the MMA issuer (on the leader CTA)
@@ -306,11 +309,6 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (lane == 0) {
         if (PAIR && !leader) mbar_arrive_remote(smem_u32(tmem_empty_bar + buf), 0);
         else mbar_arrive(smem_u32(tmem_empty_bar + buf));
-      }
-      if (SAMPLE && valid) {
-        float4* o = reinterpret_cast<float4*>(p.sample_out + ((size_t)q * p.num_slots + slot) * CHUNKS);
-        o[0] = make_float4(cmax[0], cmax[1], cmax[2], cmax[3]);
-        o[1] = make_float4(cmax[4], cmax[5], cmax[6], cmax[7]);
       }
     }
     if (!SAMPLE && valid) p.seg_cnt[(size_t)q * p.nslices + slice] = my_cnt;
