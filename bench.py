@@ -162,6 +162,37 @@ def bench_pooling(peaks, iters=20):
     return out
 
 
+def batch_sweep(index, lib, peaks, n_total, d, k, nqs, steps=10):
+    """Same search at other query-batch sizes: nq <= ~250 is the HBM-bound regime (catalog streamed once
+    per batch), larger batches are tensor-bound.  Device-resident timing, scan kernel timed by events."""
+    from two_tower_model_v2_b200 import _native
+    dp = int(lib.tt_flat_pitch(d))
+    out = []
+    for nq in nqs:
+        g = torch.Generator(device="cuda").manual_seed(4321 + nq)
+        qs = torch.randn((steps + 3, nq, d), device="cuda", generator=g)
+        for i in range(3):
+            index.search_device(qs[i], k)
+        _native.check(lib.tt_profile_scan_arm(steps), "arm")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        nunc = [index.search_device(qs[i], k)[3] for i in range(3, 3 + steps)]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        sm = torch.empty(steps, dtype=torch.float32)
+        n = lib.tt_profile_scan_read(sm.data_ptr(), steps)
+        scan = float(sm[:n].mean())
+        gbs = n_total * dp * 2 / scan / 1e6
+        tfl = 2.0 * nq * n_total * d / scan / 1e9
+        out.append({"nq": nq, "queries_per_s": nq / ms * 1e3, "ms_per_step": ms, "scan_ms": scan,
+                    "scan_hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"], "scan_bf16_tflops": tfl,
+                    "tensor_frac_sustained": tfl / peaks["bf16_tflops_sustained"],
+                    "uncertified": int(torch.stack(nunc).sum().item())})
+    return out
+
+
 def cpu_baseline_search(n_total, d, nq, k, sample_rows=1 << 20, reps=2):
     """CPU port of the reference search path (faiss-cpu IndexFlatIP is not installable: blocked fp32
     sgemm + top-k, what faiss does for nq >= 20) on a bounded sample of the catalog, all host threads."""
@@ -225,7 +256,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nq", type=int, default=int(os.environ.get("TT_BENCH_NQ", "128")), help="queries per step")
+    ap.add_argument("--nq", type=int, default=int(os.environ.get("TT_BENCH_NQ", "4096")), help="queries per step")
     ap.add_argument("--catalog-rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=384)
     ap.add_argument("--topk", type=int, default=100)
@@ -347,7 +378,8 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "uncertified_queries": uncertified,
             "roofline": roofline, "clocks": clk.summary()}
     if world == 1 and not args.no_secondary:
-        line["secondary"] = {"pooling": bench_pooling(peaks)}
+        line["secondary"] = {"pooling": bench_pooling(peaks),
+                             "query_batch_sweep": batch_sweep(index, lib, peaks, n_total, d, k, [1, 128, 1024])}
         line["cpu_baseline"] = cpu_baseline_search(n_total, d, nq, k)
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -119,9 +119,10 @@ size_t tt_flat_search_workspace_bytes(int64_t N, int D, int nq, int K);
  *                         vector_db.py:159)
  *   scores  f32 [nq, K]   fp32 inner products, descending
  *   ids     i64 [nq, K]   row index + id_offset; ties ordered by ascending id
- *   flags   i32 [nq]      1 = top-K certified exact, 0 = this query must be re-run through
- *                         tt_flat_search_exact (never observed on exchangeable data)
- *   n_uncertified i32 [1] number of zeros in flags
+ *   flags   i32 [nq]      1 = top-K certified exact; <= 0 = this query must be re-run through
+ *                         tt_flat_search_exact (value = -(reason bits): 1 candidate list overflow, 2 fewer
+ *                         than K candidates, 4 score self-check failed, 8 threshold above the prune cutoff)
+ *   n_uncertified i32 [1] number of flags != 1
  * Scores come from a bf16 tensor-core scan (tcgen05) that over-fetches a candidate set, followed
  * by fp32 rescoring of every candidate; the certificate proves no row outside the candidate set
  * can belong to the fp32 top-K.  Asynchronous on `stream`. */
@@ -160,6 +161,11 @@ int tt_profile_scan_read(float* ms_out, int max_out);
  * target_candidates, candidate_capacity, sample_stride, sample_slots, sample_rank, main_slices,
  * segment_capacity, smem_bytes. */
 int tt_flat_plan_describe(int64_t N, int D, int nq, int K, int32_t* out16);
+
+/* Diagnostic: after a tt_flat_search call that used `workspace`, copy out every query's scan threshold
+ * (bf16-score domain) and its candidate count (device pointers thr_out f32[nq], cnt_out i32[nq]). */
+int tt_flat_debug_read(const void* workspace, int64_t N, int D, int nq, int K,
+                       float* thr_out, int32_t* cnt_out, void* stream);
 
 /* Diagnostic / parity-test entry: the raw bf16 tensor-core scores of EVERY row of a small catalog
  * (N <= 2^22), out f32 [nq, N] = <bf16(qn), Xh[r]> with fp32 accumulation, as the scan kernel's

@@ -28,7 +28,7 @@ def check(idx, x, q, k, expect_certified=True):
     scores, ids, flags, nunc = idx.search_device(qd, k)
     n_bad = int(nunc.item())
     if n_bad:
-        qsel = torch.nonzero(flags == 0).flatten().to(torch.int32)
+        qsel = torch.nonzero(flags != 1).flatten().to(torch.int32)
         idx.search_exact_device(qd, k, scores, ids, qsel)
     xn, qn = fo.normalize_rows(x), fo.normalize_rows(q)
     rs, ri = fo.search(xn, qn, k)

@@ -33,9 +33,11 @@ def main():
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         torch.cuda.synchronize()
         nunc = []
+        flags_all = []
         e0.record()
         for i in range(3, 3 + steps):
-            nunc.append(index.search_device(qs[i], k)[3])
+            out = index.search_device(qs[i], k)
+            nunc.append(out[3]); flags_all.append(out[2])
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
@@ -46,7 +48,8 @@ def main():
                "scan_hbm_gbs": n_total * dp * 2 / scan / 1e6, "scan_tflops": 2.0 * nq * n_total * d / scan / 1e9,
                "hbm_frac": n_total * dp * 2 / scan / 1e6 / peaks["hbm_gbs"],
                "tensor_frac_sustained": 2.0 * nq * n_total * d / scan / 1e9 / peaks["bf16_tflops_sustained"],
-               "uncertified": int(torch.stack(nunc).sum().item())}
+               "uncertified": int(torch.stack(nunc).sum().item()),
+               "reasons": sorted(set((-f[f != 1]).tolist()) if False else torch.unique(-torch.cat(flags_all)[torch.cat(flags_all) != 1]).tolist())}
         rows.append(rec)
         print(json.dumps(rec), flush=True)
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)

@@ -38,6 +38,7 @@ SIGNATURES = {
     "tt_profile_scan_arm": (c_int, [c_int]),
     "tt_profile_scan_read": (c_int, [c_void_p, c_int]),
     "tt_flat_plan_describe": (c_int, [c_int64, c_int, c_int, c_int, c_void_p]),
+    "tt_flat_debug_read": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tt_flat_scan_scores_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "tt_flat_scan_scores": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t,
                                     c_void_p]),

@@ -191,3 +191,31 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_plan_describe(int6
   for (int i = 0; i < 16; ++i) out16[i] = v[i];
   return TT_OK;
 }
+
+// Diagnostic: after tt_flat_search on `workspace`, copy out each query's scan threshold and its total
+// number of candidates (sum over slices, before capacity clamping).  Device pointers.
+namespace tt {
+__global__ void debug_read_kernel(const float* thr, const unsigned int* seg_cnt, int nslices, int nq,
+                                  float* thr_out, int* cnt_out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  unsigned int t = 0;
+  for (int s = 0; s < nslices; ++s) t += seg_cnt[(size_t)q * nslices + s];
+  thr_out[q] = thr[q];
+  cnt_out[q] = (int)t;
+}
+}  // namespace tt
+
+extern "C" __attribute__((visibility("default"))) int tt_flat_debug_read(const void* workspace, int64_t N, int D, int nq, int K,
+                                                        float* thr_out, int32_t* cnt_out, void* stream) {
+  TT_CHECK_ARG(workspace && thr_out && cnt_out && N >= 1 && D >= 1 && nq >= 1 && K >= 1, "bad argument");
+  const ScanPlan pl = make_scan_plan(N, D, nq, K);
+  TT_CHECK_ARG(!pl.route_exact, "this (N, K) is served by the exact path: no thresholds");
+  const SearchWs w = search_ws_layout(pl, D, nq);
+  const unsigned char* ws = reinterpret_cast<const unsigned char*>(workspace);
+  debug_read_kernel<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float*>(ws + w.thr), reinterpret_cast<const unsigned int*>(ws + w.cnt), pl.main_slices, nq,
+      thr_out, cnt_out);
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}

@@ -286,9 +286,14 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const float m1 = max_tree(v1);
           if (SAMPLE) {
             if (valid) *reinterpret_cast<float2*>(sample_row + c) = make_float2(m0, m1);
-          } else if (__any_sync(0xffffffffu, fmaxf(m0, m1) >= thr)) {   // rare
-            append_columns(taddr0 + (uint32_t)(c * 32), 64, thr, (uint32_t)row0 + (uint32_t)(c * 32), my_cand, my_cnt,
-                           (unsigned int)p.seg_cap);
+          } else {
+            // rare: some column of a chunk qualifies for some lane -> re-read just that chunk
+            if (__any_sync(0xffffffffu, m0 >= thr))
+              append_columns(taddr0 + (uint32_t)(c * 32), 32, thr, (uint32_t)row0 + (uint32_t)(c * 32), my_cand, my_cnt,
+                             (unsigned int)p.seg_cap);
+            if (__any_sync(0xffffffffu, m1 >= thr))
+              append_columns(taddr0 + (uint32_t)(c * 32 + 32), 32, thr, (uint32_t)row0 + (uint32_t)(c * 32 + 32), my_cand,
+                             my_cnt, (unsigned int)p.seg_cap);
           }
         }
       } else {
@@ -503,7 +508,10 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   bool reliable = false;
   const int Tmax = FINALIZE_MAX_CAND / 4;
   {
-    int T = 6 * K < 256 ? 256 : 6 * K;   // extra candidates are cheap (finalize prunes before rescoring)
+    // ~10K candidates: with r' ~ 16 the count is ~Gamma(16)-distributed around T, and the certificate
+    // needs about K + 2*eps*density (~2.2K at N = 1e7, K = 100) of them: P(fail) ~ 1e-6 per query.
+    // Extra candidates are cheap (8-byte append; finalize prunes before rescoring).
+    int T = 10 * K < 256 ? 256 : 10 * K;
     if (T > Tmax) T = Tmax;
     // (a) r' ~ 16 from a sparse sample; small catalogs / large K fall through to denser samples
     for (int stride = T / 16; !reliable && stride >= 1; stride /= 2) reliable = try_plan(T, stride);

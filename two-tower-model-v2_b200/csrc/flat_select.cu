@@ -193,9 +193,15 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
   }
   if (threadIdx.x == 0) {
     // Rows the scan did not report have a bf16 score < thr; they are harmless iff thr <= cutoff.
-    bool ok = !overflow && n >= K && !any_bad;
-    if (ok && !(t == -INFINITY)) ok = cutoff >= t;
-    flags[q] = ok ? 1 : 0;
+    // flags: 1 = certified; otherwise -(reason bits): 1 list overflow, 2 fewer than K candidates,
+    // 4 tensor-core/fp32 score mismatch beyond eps, 8 prune cutoff below the scan threshold.
+    int why = 0;
+    if (overflow) why |= 1;
+    if (n < K) why |= 2;
+    if (any_bad) why |= 4;
+    if (n >= K && !(t == -INFINITY) && !(cutoff >= t)) why |= 8;
+    const bool ok = why == 0;
+    flags[q] = ok ? 1 : -why;
     if (!ok) atomicAdd(n_uncertified, 1);
   }
 }

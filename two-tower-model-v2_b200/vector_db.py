@@ -221,7 +221,7 @@ class FlatIPIndex:
         scores, ids, flags, nunc = self.search_device(q, k)
         n_bad = int(nunc.item())
         if n_bad:
-            qsel = torch.nonzero(flags == 0).flatten().to(torch.int32)
+            qsel = torch.nonzero(flags != 1).flatten().to(torch.int32)
             self.search_exact_device(q, k, scores, ids, qsel)
         return scores, ids, n_bad
 
