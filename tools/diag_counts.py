@@ -10,10 +10,12 @@ from two_tower_model_v2_b200 import _native, ops
 n_total, d, nq, k = int(sys.argv[1]), 384, int(sys.argv[2]), 100
 lib = _native.load()
 index, lo, hi = bench.make_shard(n_total, d, 1, 0)
-g = torch.Generator(device="cuda").manual_seed(7)
+seed = int(sys.argv[4]) if len(sys.argv) > 4 else 7
+g = torch.Generator(device="cuda").manual_seed(seed)
+qs_all = torch.randn((int(sys.argv[3]) if len(sys.argv) > 3 else 8, nq, d), device="cuda", generator=g)
 allc, allf = [], []
 for it in range(int(sys.argv[3]) if len(sys.argv) > 3 else 8):
-    q = torch.randn((nq, d), device="cuda", generator=g)
+    q = qs_all[it]
     s, i, flags, nunc = index.search_device(q, k)
     ws = index._workspace(nq, k)
     thr = torch.empty(nq, device="cuda"); cnt = torch.empty(nq, device="cuda", dtype=torch.int32)
@@ -21,7 +23,8 @@ for it in range(int(sys.argv[3]) if len(sys.argv) > 3 else 8):
     allc.append(cnt.clone()); allf.append(flags.clone())
     bad = torch.nonzero(flags != 1).flatten()
     for b in bad.tolist():
-        print("uncertified q", b, "flag", int(flags[b]), "count", int(cnt[b]), "thr", float(thr[b]), "kth score", float(s[b, k - 1]), "top", float(s[b, 0]))
+        qq = q[b] / q[b].norm(); qb = qq.to(torch.bfloat16).float(); dq = float((qb - qq).norm()); st = index.stats.tolist()
+        print("uncertified it", it, "q", b, "flag", int(flags[b]), "count", int(cnt[b]), "thr", float(thr[b]), "kth score", float(s[b, k - 1]), "top", float(s[b, 0]), "dq", dq, "stats", st[:2])
 c = torch.cat(allc).float()
 print("queries", c.numel(), "count mean", c.mean().item(), "std", c.std().item(), "min", c.min().item(), "max", c.max().item())
 print("quantiles", torch.quantile(c, torch.tensor([0.0001, 0.001, 0.01, 0.1, 0.5, 0.9, 0.99, 0.999], device="cuda")).tolist())
