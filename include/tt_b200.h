@@ -121,11 +121,12 @@ size_t tt_flat_search_workspace_bytes(int64_t N, int D, int nq, int K);
  *   ids     i64 [nq, K]   row index + id_offset; ties ordered by ascending id
  *   flags   i32 [nq]      1 = top-K certified exact; <= 0 = this query must be re-run through
  *                         tt_flat_search_exact (value = -(reason bits): 1 candidate list overflow, 2 fewer
- *                         than K candidates, 4 score self-check failed, 8 threshold above the prune cutoff)
+ *                         than K candidates, 4 score self-check failed, 8 the K-th rescored score does not clear the
+ *                         bound of the rows that were not rescored)
  *   n_uncertified i32 [1] number of flags != 1
  * Scores come from a bf16 tensor-core scan (tcgen05) that over-fetches a candidate set, followed
- * by fp32 rescoring of every candidate; the certificate proves no row outside the candidate set
- * can belong to the fp32 top-K.  Asynchronous on `stream`. */
+ * by fp32 rescoring of the candidates whose bf16 score is within reach of the K-th; the certificate
+ * proves no row that was not rescored can belong to the fp32 top-K.  Asynchronous on `stream`. */
 #define TT_FLAT_MAX_K 2048
 int tt_flat_search(const float* q, int nq,
                    const float* Xn, const void* Xh, const float* stats, int64_t N, int D,
@@ -147,6 +148,27 @@ int tt_flat_search_exact(const float* q, int nq, const int32_t* qsel, int nsel,
  * (score descending, id ascending). */
 int tt_topk_merge(const float* scores_g, const int64_t* ids_g, int G, int nq, int K,
                   float* scores, int64_t* ids, void* stream);
+
+/* Catalog sharded over G devices (north_star (3); the reference has no multi-device path).
+ * tt_flat_search_shard = tt_flat_search over this shard's rows (ids = local row + id_offset), plus
+ *   bound f32 [nq]: every row of this shard that was NOT rescored in fp32 scores strictly below bound[q]
+ *                   (-inf when every row was rescored).  The per-shard flags keep their meaning, but bits 2
+ *                   and 8 (local K-th score checks) are superseded by the global certificate below.
+ * Each rank packs {scores f32[nq,K] | ids i64[nq,K] | bound f32[nq] | flags i32[nq]} into one byte record
+ * (lists shorter than K padded with score -inf / id -1); ONE all-gather of the records gives `gathered`
+ * (G records, rank_stride bytes apart, fields at the given byte offsets).
+ * tt_shard_merge merges the G sorted lists (score descending, id ascending) into scores/ids [nq,K] and
+ * certifies each query: exact iff the merged K-th score >= max over shards of bound[q] and no shard
+ * reported a candidate overflow (1) or a score self-check failure (4); flags/n_uncertified as in
+ * tt_flat_search - an uncertified query is re-run through tt_flat_search_exact on every shard. */
+int tt_flat_search_shard(const float* q, int nq,
+                         const float* Xn, const void* Xh, const float* stats, int64_t N, int D,
+                         int K, int64_t id_offset,
+                         float* scores, int64_t* ids, int32_t* flags, int32_t* n_uncertified, float* bound,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int tt_shard_merge(const void* gathered, size_t rank_stride, size_t off_scores, size_t off_ids,
+                   size_t off_bound, size_t off_flags, int G, int nq, int K,
+                   float* scores, int64_t* ids, int32_t* flags, int32_t* n_uncertified, void* stream);
 
 /* Measurement hooks (bench.py).  tt_kernel_launch_count: kernels this library has launched in this
  * process.  tt_profile_scan_arm(n): the next n main-scan launches of tt_flat_search are bracketed by

@@ -198,3 +198,67 @@ def test_1m_catalog_properties():
         rs, ri = fo.search(xn, qn, k, block=1 << 18)
         ok, msg = fo.compare_topk(s[sub].cpu().numpy(), i[sub].cpu().numpy(), rs, ri, xn, qn)
         assert ok, msg
+
+
+# ---- sharded path on one device: G shards of one catalog, records stacked as an all-gather would -----
+def _shard_records(x, q, k, G):
+    import two_tower_model_v2_b200 as pkg
+    from two_tower_model_v2_b200.sharded import record_layout, record_views
+    N, nq = x.shape[0], q.shape[0]
+    lay = record_layout(nq, k)
+    gathered = torch.zeros((G, lay.nbytes), dtype=torch.uint8, device=dev())
+    qd = torch.from_numpy(q).to(dev())
+    shards = []
+    for g in range(G):
+        lo, hi = pkg.shard_bounds(N, G, g)
+        idx = build(x[lo:hi])
+        idx.id_offset = lo
+        s, i, b, f = record_views(gathered[g], lay, nq, k)
+        kl = min(k, hi - lo)
+        if kl < k:
+            s.fill_(float("-inf")); i.fill_(-1)
+        idx.search_shard_into(qd, kl, s, i, b, f)
+        shards.append(idx)
+    return gathered, lay, shards
+
+
+@pytest.mark.parametrize("N,D,nq,k,G", [(40000, 64, 33, 100, 4), (70000, 384, 130, 10, 8), (900, 32, 5, 300, 3)])
+def test_shard_merge_matches_oracle_and_numpy_merge(N, D, nq, k, G):
+    from test_sharded_gloo import _merge_oracle
+    from two_tower_model_v2_b200 import ops
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((N, D)).astype(np.float32)
+    q = rng.standard_normal((nq, D)).astype(np.float32)
+    gathered, lay, _ = _shard_records(x, q, k, G)
+    s, i, flags, nunc = ops.shard_merge(gathered, lay.off_scores, lay.off_ids, lay.off_bound, lay.off_flags, nq, k)
+    ns, ni, nf, nn = _merge_oracle(gathered.cpu(), lay, nq, k)
+    assert torch.equal(s.cpu(), ns) and torch.equal(i.cpu(), ni) and torch.equal(flags.cpu(), nf)
+    assert int(nunc.item()) == nn == 0
+    xn, qn = fo.normalize_rows(x), fo.normalize_rows(q)
+    rs, ri = fo.search(xn, qn, k)
+    ok, msg = fo.compare_topk(s.cpu().numpy(), i.cpu().numpy(), rs, ri, xn, qn)
+    assert ok, msg
+
+
+def test_shard_merge_global_certificate_rejects_and_recovers():
+    """A shard whose bound exceeds the merged K-th score must flag the query (reason 8); overflow (1) and
+    self-check (4) bits of any shard propagate; local 'fewer than K' (2) alone does not."""
+    from two_tower_model_v2_b200 import ops
+    from two_tower_model_v2_b200.sharded import record_views
+    rng = np.random.default_rng(12)
+    N, D, nq, k, G = 30000, 64, 8, 50, 4
+    x = rng.standard_normal((N, D)).astype(np.float32)
+    q = rng.standard_normal((nq, D)).astype(np.float32)
+    gathered, lay, _ = _shard_records(x, q, k, G)
+    sg, ig, bg, fg = record_views(gathered, lay, nq, k)
+    merged = ops.shard_merge(gathered, lay.off_scores, lay.off_ids, lay.off_bound, lay.off_flags, nq, k)
+    kth = merged[0][:, k - 1].clone()
+    bg[1, 0] = kth[0] + 1e-3          # shard 1 cannot exclude an unseen row above the K-th score of query 0
+    bg[2, 1] = kth[1]                 # equality still certifies (unseen rows score strictly below the bound)
+    fg[3, 2] = -1                     # overflow on shard 3, query 2
+    fg[0, 3] = -4                     # self-check failure on shard 0, query 3
+    fg[0, 4] = -2                     # locally short list only: superseded by the global check
+    fg[1, 5] = -8                     # local K-th check only: superseded too
+    s, i, flags, nunc = ops.shard_merge(gathered, lay.off_scores, lay.off_ids, lay.off_bound, lay.off_flags, nq, k)
+    assert flags.cpu().tolist() == [-8, 1, -1, -4, 1, 1, 1, 1]
+    assert int(nunc.item()) == 3

@@ -81,10 +81,10 @@ extern "C" __attribute__((visibility("default"))) size_t tt_flat_search_workspac
   return search_ws_layout(pl, D, nq).total;
 }
 
-extern "C" __attribute__((visibility("default"))) int tt_flat_search(const float* q, int nq, const float* Xn, const void* Xh, const float* stats,
-                              int64_t N, int D, int K, int64_t id_offset, float* scores, int64_t* ids,
-                              int32_t* flags, int32_t* n_uncertified, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+static int flat_search_impl(const float* q, int nq, const float* Xn, const void* Xh, const float* stats,
+                            int64_t N, int D, int K, int64_t id_offset, float* scores, int64_t* ids,
+                            int32_t* flags, int32_t* n_uncertified, float* bound, void* workspace,
+                            size_t workspace_bytes, void* stream) {
   TT_CHECK_ARG(q && Xn && Xh && stats && scores && ids && flags && n_uncertified, "null pointer");
   TT_CHECK_ARG(nq >= 0, "nq < 0");
   TT_CHECK_ARG(N >= 1 && N < (1LL << 31), "need 1 <= N < 2^31 rows per shard");
@@ -106,6 +106,10 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_search(const float
     // K is too large a fraction of N for a sampled threshold: the fp32 exact path serves the batch.
     fill_int_kernel<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, 1);
     TT_CHECK_LAUNCH();
+    if (bound) {   // the exact path scores every row: nothing is left unbounded
+      fill_int_kernel<<<(nq + 255) / 256, 256, 0, st>>>(reinterpret_cast<int*>(bound), nq, (int)0xff800000);
+      TT_CHECK_LAUNCH();
+    }
     return tt_flat_search_exact(q, nq, nullptr, nq, Xn, N, D, K, id_offset, scores, ids, workspace,
                                 workspace_bytes, stream);
   }
@@ -124,7 +128,24 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_search(const float
   if (int e = launch_prep_queries(q, nq, pl.nq_pad, D, pl.Dp, stats, qn, qh, eps, st)) return e;
   if (int e = launch_scan(pl, qh, Xh, N, nq, thr, cnt, cand, sample, st)) return e;
   return launch_finalize(pl, qn, Xn, N, D, nq, K, id_offset, thr, eps, cnt, cand, scores,
-                         reinterpret_cast<long long*>(ids), flags, n_uncertified, st);
+                         reinterpret_cast<long long*>(ids), flags, n_uncertified, bound, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_flat_search(const float* q, int nq, const float* Xn, const void* Xh, const float* stats,
+                              int64_t N, int D, int K, int64_t id_offset, float* scores, int64_t* ids,
+                              int32_t* flags, int32_t* n_uncertified, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  return flat_search_impl(q, nq, Xn, Xh, stats, N, D, K, id_offset, scores, ids, flags, n_uncertified, nullptr,
+                          workspace, workspace_bytes, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_flat_search_shard(const float* q, int nq, const float* Xn, const void* Xh, const float* stats,
+                              int64_t N, int D, int K, int64_t id_offset, float* scores, int64_t* ids,
+                              int32_t* flags, int32_t* n_uncertified, float* bound, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  TT_CHECK_ARG(bound != nullptr, "null bound");
+  return flat_search_impl(q, nq, Xn, Xh, stats, N, D, K, id_offset, scores, ids, flags, n_uncertified, bound,
+                          workspace, workspace_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -25,6 +25,7 @@ struct ScanPlan {
   bool route_exact;    // true: K is too large a fraction of N for a sampled threshold -> fp32 exact path
   int main_slices;
   int sample_stride, sample_slots, sample_slices, sample_rank;
+  bool sample_tile_max;  // sample pass records one maximum per sampled tile (else one per 32-row chunk)
 };
 
 ScanPlan make_scan_plan(long long N, int D, int nq, int K);
@@ -40,7 +41,7 @@ int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N,
 int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long long N, int D, int nq, int K,
                     long long id_offset, const float* thr, const float* eps, const unsigned int* seg_cnt,
                     const void* cand, float* scores, long long* ids, int* flags, int* n_uncertified,
-                    cudaStream_t st);
+                    float* bound_out, cudaStream_t st);
 
 // Optional device-side timing of the main scan kernel (bench.py roofline): when armed, launch_scan
 // brackets the main scan launch with a pair of CUDA events on the launching stream.

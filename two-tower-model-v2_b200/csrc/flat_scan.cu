@@ -68,19 +68,28 @@ struct ScanParams {
   uint2* cand;            // [nq, nslices, seg_cap]  (score bits, row)
   int seg_cap;
   // SAMPLE
-  float* sample_out;      // [nq_pad, num_slots, 8] maxima of the 32-row chunks of every sampled tile
+  float* sample_out;      // chunk mode: [nq_pad, num_slots, 8] maxima of the 32-row chunks of every sampled tile
+                          // tile mode : [num_slots, sample_ld] maximum of every sampled tile (query fastest)
+  int sample_tile_max;    // 1 = tile mode
+  int sample_ld;          // tile mode: leading dimension (nq_pad)
 };
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3 (sm_100)
+  return r;
+}
 __device__ __forceinline__ float max_tree(const uint32_t (&v)[32]) {
-  float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+  float m[4];
 #pragma unroll
-  for (int j = 4; j < 32; j += 4) {
-    m0 = fmaxf(m0, __uint_as_float(v[j]));
-    m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
-    m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
-    m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
-  }
-  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  for (int i = 0; i < 4; ++i) m[i] = max3(__uint_as_float(v[i]), __uint_as_float(v[i + 4]), __uint_as_float(v[i + 8]));
+#pragma unroll
+  for (int j = 12; j < 28; j += 8)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = max3(m[i], __uint_as_float(v[j + i]), __uint_as_float(v[j + i + 4]));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m[i] = fmaxf(m[i], __uint_as_float(v[28 + i]));
+  return max3(fmaxf(m[0], m[1]), m[2], m[3]);
 }
 
 // Slow paths of the epilogue (warp-collective: every lane of the warp must call them).  They read
@@ -114,6 +123,20 @@ __device__ __noinline__ float max_columns(uint32_t taddr, int ncols) {
     for (int j = 0; j < 8; ++j) if (c + j < ncols) m = fmaxf(m, __uint_as_float(v[j]));
   }
   return m;
+}
+
+// Append every register-resident column that reaches the threshold.  Predicated straight-line code:
+// all lanes run it, each on its own (query, slice) segment.  On overflow the last slot is overwritten
+// and the count keeps growing, which finalize reports as "overflow" (exact re-run of that query).
+__device__ __forceinline__ void append_regs(const uint32_t (&v)[32], float thr, uint32_t row_base, uint2* seg,
+                                            unsigned int& cnt, unsigned int last) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (__uint_as_float(v[j]) >= thr) {
+      seg[min(cnt, last)] = make_uint2(v[j], row_base + (uint32_t)j);
+      ++cnt;
+    }
+  }
 }
 
 template <int BLOCK_M, bool SAMPLE, bool PAIR>
@@ -258,6 +281,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (!SAMPLE && valid) thr = __ldg(p.thr + q);
     uint2* my_cand = SAMPLE ? nullptr : (p.cand + ((size_t)(valid ? q : 0) * p.nslices + slice) * p.seg_cap);
     unsigned int my_cnt = 0;
+    const unsigned int seg_last = (unsigned int)(p.seg_cap > 0 ? p.seg_cap - 1 : 0);
 
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
@@ -271,39 +295,64 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float* sample_row = SAMPLE ? (p.sample_out + ((size_t)(valid ? q : 0) * p.num_slots + slot) * CHUNKS) : nullptr;
 
       if (ncols == BLOCK_N) {
-        // ---- full tile.  Fast path: two 32-column chunks per TMEM wait, max-reduce, one compare.  The
-        // loop is deliberately NOT unrolled and the rare "some column qualifies" path re-reads the chunk
-        // from TMEM 8 columns at a time in a small loop: the whole epilogue stays a few hundred
-        // instructions (an unrolled 256-way compare/append thrashed the instruction cache).
-#pragma unroll 1
-        for (int c = 0; c < CHUNKS; c += 2) {
-          uint32_t v0[32], v1[32];
-          __syncwarp();
-          tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v0);
-          tmem_ld_32x32(taddr0 + (uint32_t)(c * 32 + 32), v1);
-          tmem_ld_wait();
+        // ---- full tile.  64 accumulator columns per step, software-pipelined over two register sets:
+        // the tcgen05.ld of the next 64 columns is in flight while the current 64 are reduced (3-input
+        // max tree) and compared once against the threshold.  The loop stays rolled (a fully unrolled
+        // 256-way compare/append thrashed the instruction cache).
+        uint32_t a0[32], a1[32], b0[32], b1[32];
+        float tile_max = -INFINITY;
+        auto consume = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int c) {
           const float m0 = max_tree(v0);
           const float m1 = max_tree(v1);
           if (SAMPLE) {
-            if (valid) *reinterpret_cast<float2*>(sample_row + c) = make_float2(m0, m1);
-          } else {
-            // rare: some column of a chunk qualifies for some lane -> re-read just that chunk
-            if (__any_sync(0xffffffffu, m0 >= thr))
-              append_columns(taddr0 + (uint32_t)(c * 32), 32, thr, (uint32_t)row0 + (uint32_t)(c * 32), my_cand, my_cnt,
-                             (unsigned int)p.seg_cap);
-            if (__any_sync(0xffffffffu, m1 >= thr))
-              append_columns(taddr0 + (uint32_t)(c * 32 + 32), 32, thr, (uint32_t)row0 + (uint32_t)(c * 32 + 32), my_cand,
-                             my_cnt, (unsigned int)p.seg_cap);
+            if (p.sample_tile_max) tile_max = fmaxf(tile_max, fmaxf(m0, m1));
+            else if (valid) *reinterpret_cast<float2*>(sample_row + c) = make_float2(m0, m1);
+          } else if (__any_sync(0xffffffffu, fmaxf(m0, m1) >= thr)) {
+            // rare (a few % of the steps): some column qualifies for some lane.  The values are still in
+            // registers: one predicated compare/append per column, shared by both halves through a rolled
+            // 2-iteration loop so the code stays small.
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+              uint32_t s[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s[j] = h ? v1[j] : v0[j];
+              if (__any_sync(0xffffffffu, (h ? m1 : m0) >= thr))
+                append_regs(s, thr, (uint32_t)row0 + (uint32_t)((c + h) * 32), my_cand, my_cnt, seg_last);
+            }
           }
+        };
+        __syncwarp();
+        tmem_ld_32x32(taddr0, a0);
+        tmem_ld_32x32(taddr0 + 32u, a1);
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; c += 4) {
+          tmem_ld_wait();
+          __syncwarp();
+          tmem_ld_32x32(taddr0 + (uint32_t)(c * 32 + 64), b0);
+          tmem_ld_32x32(taddr0 + (uint32_t)(c * 32 + 96), b1);
+          consume(a0, a1, c);
+          tmem_ld_wait();
+          if (c + 4 < CHUNKS) {
+            __syncwarp();
+            tmem_ld_32x32(taddr0 + (uint32_t)(c * 32 + 128), a0);
+            tmem_ld_32x32(taddr0 + (uint32_t)(c * 32 + 160), a1);
+          }
+          consume(b0, b1, c + 2);
         }
+        if (SAMPLE && p.sample_tile_max && q_local >= 0)
+          p.sample_out[(size_t)slot * p.sample_ld + (size_t)(qb * BLOCK_M + q_local)] = tile_max;
       } else {
         // ---- partial last tile: columns >= ncols are zero-filled padding rows ----------------------
         if (SAMPLE) {
+          float tile_max = -INFINITY;
           for (int c = 0; c < CHUNKS; ++c) {
             const int limit = min(32, ncols - c * 32);
             const float m = (limit > 0) ? max_columns(taddr0 + (uint32_t)(c * 32), limit) : -INFINITY;
-            if (valid) sample_row[c] = m;
+            if (p.sample_tile_max) tile_max = fmaxf(tile_max, m);
+            else if (valid) sample_row[c] = m;
           }
+          if (p.sample_tile_max && q_local >= 0)
+            p.sample_out[(size_t)slot * p.sample_ld + (size_t)(qb * BLOCK_M + q_local)] = tile_max;
         } else {
           append_columns(taddr0, ncols, thr, (uint32_t)row0, my_cand, my_cnt, (unsigned int)p.seg_cap);
         }
@@ -394,6 +443,54 @@ select_threshold_kernel(const float* __restrict__ sample, int n, int npad, int r
     __syncthreads();
   }
   if (threadIdx.x == 0) thr[q] = result;
+}
+
+// Tile mode: thr[q] = r-th largest of the sampled tile maxima sample[slot][q] (query fastest), one warp
+// per query.  The CTA stages a [slots x WQ] panel through shared memory with sector-sized reads, then
+// every warp runs r rounds of arg-max over its own column (each lane caches the best of its strided
+// values; only the winning lane rescans).  No block-wide barrier inside the rounds.
+constexpr int SEL_WQ = 8;   // queries (warps) per CTA
+__global__ void __launch_bounds__(SEL_WQ * 32)
+select_threshold_tile_kernel(const float* __restrict__ sample, int slots, int ld, int nq, int r, float* __restrict__ thr) {
+  extern __shared__ float sv[];   // [SEL_WQ][slots]
+  const int q0 = blockIdx.x * SEL_WQ;
+  for (int e = threadIdx.x; e < slots * SEL_WQ; e += blockDim.x) {
+    const int i = e / SEL_WQ, qq = e % SEL_WQ;
+    sv[qq * slots + i] = (q0 + qq < ld) ? sample[(size_t)i * ld + q0 + qq] : -INFINITY;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = q0 + warp;
+  if (q >= nq) return;
+  float* v = sv + warp * slots;
+  float best = -INFINITY;
+  int bi = -1;
+  for (int i = lane; i < slots; i += 32) {
+    const float x = v[i];
+    if (x > best) { best = x; bi = i; }
+  }
+  float result = -INFINITY;
+  for (int round = 0; round < r; ++round) {
+    float wb = best;
+    int wi = bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, wb, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (ob > wb || (ob == wb && oi > wi)) { wb = ob; wi = oi; }
+    }
+    result = (wi >= 0) ? wb : -INFINITY;
+    if (wi >= 0 && wi == bi) {      // this lane owns the winner: drop it and rescan its own values
+      v[wi] = -INFINITY;
+      best = -INFINITY; bi = -1;
+      for (int i = lane; i < slots; i += 32) {
+        const float x = v[i];
+        if (x > best) { best = x; bi = i; }
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) thr[q] = result;
 }
 
 __global__ void fill_kernel(float* p, int n, float v) {
@@ -493,7 +590,10 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
     const long long ns_rows = last_slot * BLOCK_N + rem;
     // r' = rank (within the sample) of the score that ~T rows of the whole catalog reach
     const double rp = (double)T * (double)ns_rows / (double)N;
-    const double nvals = (double)(slots * CHUNKS);
+    // One maximum per sampled tile is enough (and 8x less data to write, read and select from) when the
+    // top-r' sampled rows rarely share a tile; otherwise keep one maximum per 32-row chunk.
+    const bool tile_mode = slots >= 128 && rp <= (double)slots / 4.0 && rp <= 64.0;
+    const double nvals = tile_mode ? (double)slots : (double)(slots * CHUNKS);
     if (rp < 11.5 || rp > 1.5 * nvals) return false;
     if (nvals < 128.0 && stride > 1) return false;   // too few chunk maxima for a stable quantile: sample denser
     // The top-r' sampled rows occupy about nvals*(1-exp(-r'/nvals)) distinct 32-row chunks, so that is
@@ -503,6 +603,7 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
     pl.sample_stride = stride;
     pl.sample_slots = (int)slots;
     pl.sample_rank = (int)(r + 0.5) < 1 ? 1 : (int)(r + 0.5);
+    pl.sample_tile_max = tile_mode;
     return true;
   };
   bool reliable = false;
@@ -535,7 +636,7 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   pl.use_threshold = reliable;
   const long long slice_rows = ((long long)(pl.num_tiles + pl.main_slices - 1) / pl.main_slices) * BLOCK_N;
   if (!reliable) {
-    pl.sample_stride = 1; pl.sample_slots = 1; pl.sample_rank = 1; pl.target = 0;
+    pl.sample_stride = 1; pl.sample_slots = 1; pl.sample_rank = 1; pl.target = 0; pl.sample_tile_max = false;
     if (N <= FINALIZE_MAX_CAND) {
       C = 2048;
       while (C < N) C <<= 1;
@@ -601,13 +702,22 @@ int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N,
 
   if (pl.use_threshold) {
     sp.num_slots = pl.sample_slots; sp.tile_stride = pl.sample_stride; sp.nslices = pl.sample_slices;
+    sp.sample_tile_max = pl.sample_tile_max ? 1 : 0;
+    sp.sample_ld = pl.nq_pad;
     if (int e = launch_scan_mode<true>(pl, tq, tx, sp, pl.sample_slices * pl.nqu, st)) return e;
-    const int nvals = pl.sample_slots * CHUNKS;
-    int npad = 1;
-    while (npad < nvals) npad <<= 1;
-    const size_t sm = (size_t)npad * sizeof(float);
-    TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    select_threshold_kernel<<<nq, 256, sm, st>>>(sample_buf, nvals, npad, pl.sample_rank, thr);
+    if (pl.sample_tile_max) {
+      const size_t sm = (size_t)pl.sample_slots * SEL_WQ * sizeof(float);
+      TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      select_threshold_tile_kernel<<<(nq + SEL_WQ - 1) / SEL_WQ, SEL_WQ * 32, sm, st>>>(sample_buf, pl.sample_slots, pl.nq_pad,
+                                                                                       nq, pl.sample_rank, thr);
+    } else {
+      const int nvals = pl.sample_slots * CHUNKS;
+      int npad = 1;
+      while (npad < nvals) npad <<= 1;
+      const size_t sm = (size_t)npad * sizeof(float);
+      TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      select_threshold_kernel<<<nq, 256, sm, st>>>(sample_buf, nvals, npad, pl.sample_rank, thr);
+    }
     TT_CHECK_LAUNCH();
   } else {
     fill_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thr, nq, -INFINITY);

@@ -54,76 +54,145 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ qs, const fl
 
 // ------------------------------------------------------------------------------------------
 // finalize: one CTA per query.
-//   1. sort the candidate list by its bf16 tensor-core score;
-//   2. prune: with b_K the K-th largest bf16 score, only rows with bf16 score >= b_K - 2*eps can
-//      belong to the fp32 top-K (K rows have fp32 >= b_K - eps, and a row's fp32 score is below its
-//      bf16 score + eps), so only those are rescored (about K + a few dozen 1.5 KB row gathers
-//      instead of the whole over-fetched list);
-//   3. rescore the survivors in fp32 against the fp32 table, sort by (score desc, row asc), emit K;
-//   4. certificate: the prune cutoff must not fall below the scan threshold, otherwise a row the
-//      scan never reported could qualify -> flag the query for the exact path.
-__global__ void __launch_bounds__(512)
+//   1. gather the query's per-slice candidate segments (bf16 tensor-core score, row);
+//   2. b_K = K-th largest bf16 score by a 4-pass radix select (no sort of the over-fetched list);
+//   3. prune: only rows with bf16 score >= cutoff = b_K - PRUNE_MARGIN*eps are rescored (a row of the
+//      fp32 top-K scores within eps of its bf16 score, so it sits well inside that band);
+//   4. rescore the survivors in fp32 against the fp32 table; rank them by (score desc, row asc); emit K;
+//   5. certificate (a posteriori, rigorous): every row that was NOT rescored has a bf16 score below
+//      c = max(scan threshold, cutoff), hence an fp32 score below c + eps.  If the K-th best rescored
+//      fp32 score f_K >= c + eps, no such row can enter the top-K: the result is exact.  Otherwise the
+//      query is flagged and the host re-runs it through the exact path.
+constexpr int FIN_THREADS = 256;
+constexpr float PRUNE_MARGIN = 1.5f;       // in units of eps; typical |bf16 - fp32| is ~eps/25
+constexpr int RANK_BY_COUNT_MAX = 1024;    // survivors up to this many are ranked by counting, else bitonic sort
+
+__global__ void __launch_bounds__(FIN_THREADS)
 flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn, long long N, int D, int K,
                      long long id_offset, const float* __restrict__ thr, const float* __restrict__ eps,
                      const unsigned int* __restrict__ seg_cnt, const uint2* __restrict__ cand, int nslices,
                      int seg_cap, int cand_cap,
                      float* __restrict__ scores, long long* __restrict__ ids, int* __restrict__ flags,
-                     int* __restrict__ n_uncertified) {
+                     int* __restrict__ n_uncertified, float* __restrict__ bound_out) {
   extern __shared__ __align__(16) unsigned char fsm[];
   unsigned long long* key = reinterpret_cast<unsigned long long*>(fsm);
-  __shared__ int s_m, s_n, s_over;
+  float* qs = reinterpret_cast<float*>(key + cand_cap);
   __shared__ int s_off[FINALIZE_MAX_SLICES + 1];
+  __shared__ unsigned int s_hist[256];
+  __shared__ int s_wsum[FIN_THREADS / 32];
+  __shared__ int s_over, s_bad, s_digit, s_kk;
+  __shared__ float s_fk;
   const int q = blockIdx.x;
-  // ---- gather this query's per-slice candidate segments -----------------------------------------
-  if (threadIdx.x == 0) {
-    int tot = 0, over = 0;
-    for (int sl = 0; sl < nslices; ++sl) {
-      unsigned int c = seg_cnt[(size_t)q * nslices + sl];
-      if (c > (unsigned int)seg_cap) { c = (unsigned int)seg_cap; over = 1; }
-      if (tot + (int)c > cand_cap) { c = (unsigned int)(cand_cap - tot); over = 1; }
-      s_off[sl] = tot;
-      tot += (int)c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARPS = FIN_THREADS / 32;
+
+  // ---- 1. segment sizes -> offsets (parallel loads, warp-0 scan) --------------------------------
+  if (tid == 0) { s_over = 0; s_bad = 0; s_fk = -INFINITY; s_off[0] = 0; }
+  __syncthreads();
+  for (int sl = tid; sl < nslices; sl += FIN_THREADS) {
+    unsigned int c = seg_cnt[(size_t)q * nslices + sl];
+    if (c > (unsigned int)seg_cap) { c = (unsigned int)seg_cap; s_over = 1; }
+    s_off[sl + 1] = (int)c;
+  }
+  for (int d = tid; d < D; d += FIN_THREADS) qs[d] = qn[(long long)q * D + d];
+  __syncthreads();
+  if (warp == 0) {
+    int carry = 0;
+    for (int base = 0; base < nslices; base += 32) {
+      const int sl = base + lane;
+      int v = (sl < nslices) ? s_off[sl + 1] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+      int incl = carry + v;
+      if (incl > cand_cap) { incl = cand_cap; s_over = 1; }
+      if (sl < nslices) s_off[sl + 1] = incl;
+      carry = __shfl_sync(0xffffffffu, incl, 31);
     }
-    s_off[nslices] = tot;
-    s_n = tot; s_over = over; s_m = tot;
   }
   __syncthreads();
   const bool overflow = s_over != 0;
-  const int n = s_n;
-  const int P = next_pow2(n < 2 ? 2 : n);   // >= 2 keeps qs 16-byte aligned
-  float* qs = reinterpret_cast<float*>(key + P);
+  const int n = s_off[nslices];
   const float my_eps = eps[q];
   const float t = thr[q];
-  for (int d = threadIdx.x; d < D; d += blockDim.x) qs[d] = qn[(long long)q * D + d];
-  {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int sl = warp; sl < nslices; sl += nwarps) {
-      const int o = s_off[sl], c = s_off[sl + 1] - o;
-      const uint2* seg = cand + ((size_t)q * nslices + sl) * seg_cap;
-      for (int i = lane; i < c; i += 32) { const uint2 e = seg[i]; key[o + i] = make_key(__uint_as_float(e.x), e.y); }
-    }
-    for (int i = n + threadIdx.x; i < P; i += blockDim.x) key[i] = 0ull;
+
+  // ---- gather: one candidate per thread step, slice found by binary search over the offsets ------
+  for (int i = tid; i < n; i += FIN_THREADS) {
+    int lo = 0, hi = nslices;           // largest sl with s_off[sl] <= i
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
+    const uint2 e = cand[((size_t)q * nslices + lo) * seg_cap + (i - s_off[lo])];
+    key[i] = make_key(__uint_as_float(e.x), e.y);
   }
   __syncthreads();
-  bitonic_sort_desc(key, P);
 
-  // ---- prune by bf16 score -----------------------------------------------------------------
+  // ---- 2. b_K by radix select on the ordered score bits (8 bits per pass, MSB first) --------------
   float cutoff = -INFINITY;
-  if (n >= K) cutoff = key_score(key[K - 1]) - 2.f * my_eps;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const bool in = key_score(key[i]) >= cutoff;
-    const bool next_in = (i + 1 < n) && (key_score(key[i + 1]) >= cutoff);
-    if (in && !next_in) s_m = i + 1;         // sorted: exactly one boundary
+  if (n > K) {   // n == K: everything is rescored anyway
+    uint32_t prefix = 0u, mask = 0u;
+    int kk = K;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      s_hist[tid] = 0u;
+      __syncthreads();
+      for (int i = tid; i < n; i += FIN_THREADS) {
+        const uint32_t u = (uint32_t)(key[i] >> 32);
+        if ((u & mask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (warp == 0) {
+        // lane l owns bins 255-8l .. 248-8l (descending)
+        unsigned int loc[8];
+        unsigned int sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { loc[j] = s_hist[255 - 8 * lane - j]; sum += loc[j]; }
+        unsigned int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const unsigned int excl = incl - sum;
+        if (excl < (unsigned int)kk && incl >= (unsigned int)kk) {   // exactly one lane
+          unsigned int above = excl;
+          int d = 255 - 8 * lane - 7;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (above + loc[j] >= (unsigned int)kk) { d = 255 - 8 * lane - j; break; }
+            above += loc[j];
+          }
+          s_digit = d;
+          s_kk = kk - (int)above;
+        }
+      }
+      __syncthreads();
+      prefix |= (uint32_t)s_digit << shift;
+      mask |= 255u << shift;
+      kk = s_kk;
+    }
+    cutoff = ordered_to_float(prefix) - PRUNE_MARGIN * my_eps;
   }
-  __syncthreads();
-  const int m = s_m;
 
-  // ---- fp32 rescoring of the m survivors (in place) -------------------------------------------
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // ---- 3. prune: in-place compaction of the survivors (chunks of FIN_THREADS, left-moving) ---------
+  int m = n;
+  if (cutoff > -INFINITY) {
+    int out = 0;
+    for (int base = 0; base < n; base += FIN_THREADS) {
+      const int i = base + tid;
+      const unsigned long long kk64 = (i < n) ? key[i] : 0ull;
+      const bool keep = (i < n) && (key_score(kk64) >= cutoff);
+      const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) s_wsum[warp] = __popc(bal);
+      __syncthreads();                       // also orders every read of this chunk before the writes below
+      int wbase = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < NWARPS; ++w) { const int c = s_wsum[w]; if (w < warp) wbase += c; tot += c; }
+      if (keep) key[out + wbase + __popc(bal & ((1u << lane) - 1u))] = kk64;
+      out += tot;
+      __syncthreads();
+    }
+    m = out;
+  }
+
+  // ---- 4. fp32 rescoring of the m survivors (in place) --------------------------------------------
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(Xn) & 15) == 0);
   int bad = 0;   // self-check: a candidate's tensor-core score must match its fp32 rescoring within eps
   constexpr int U = 4;   // candidates rescored concurrently per warp (independent loads in flight)
-  for (int i0 = warp * U; i0 < m; i0 += nwarps * U) {
+  for (int i0 = warp * U; i0 < m; i0 += NWARPS * U) {
     uint32_t row[U];
     float bsc[U];
     bool ok[U];
@@ -131,9 +200,9 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int i = i0 + u;
-      const unsigned long long kk = (i < m) ? key[i] : 0ull;
-      row[u] = key_row(kk);
-      bsc[u] = key_score(kk);
+      const unsigned long long kk64 = (i < m) ? key[i] : 0ull;
+      row[u] = key_row(kk64);
+      bsc[u] = key_score(kk64);
       ok[u] = (i < m) && ((long long)row[u] < N);   // row >= N cannot happen unless the scan is broken
       a[u] = 0.f;
     }
@@ -176,46 +245,71 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
       }
     }
   }
-  const int P2 = next_pow2(m < 2 ? 2 : m);
-  const int any_bad = __syncthreads_or(bad);
-  for (int i = m + threadIdx.x; i < P2; i += blockDim.x) key[i] = 0ull;
+  if (bad) s_bad = 1;
   __syncthreads();
-  bitonic_sort_desc(key, P2);
 
-  for (int i = threadIdx.x; i < K; i += blockDim.x) {
-    if (i < m) {
-      scores[(long long)q * K + i] = key_score(key[i]);
-      ids[(long long)q * K + i] = (long long)key_row(key[i]) + id_offset;
-    } else {
+  // ---- 5. order the survivors by (score desc, row asc) and emit K ---------------------------------
+  if (m <= RANK_BY_COUNT_MAX) {
+    // keys are distinct (the row is part of the key): rank = number of larger keys
+    for (int i = tid; i < m; i += FIN_THREADS) {
+      const unsigned long long ki = key[i];
+      int rank = 0;
+      for (int j = 0; j < m; ++j) rank += (key[j] > ki) ? 1 : 0;
+      if (rank < K) {
+        scores[(long long)q * K + rank] = key_score(ki);
+        ids[(long long)q * K + rank] = (ki == 0ull) ? -1 : (long long)key_row(ki) + id_offset;
+        if (rank == K - 1) s_fk = key_score(ki);
+      }
+    }
+    for (int i = m + tid; i < K; i += FIN_THREADS) {
       scores[(long long)q * K + i] = -INFINITY;
       ids[(long long)q * K + i] = -1;
     }
+  } else {
+    const int P2 = next_pow2(m);
+    for (int i = m + tid; i < P2; i += FIN_THREADS) key[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(key, P2);
+    for (int i = tid; i < K; i += FIN_THREADS) {
+      if (i < m) {
+        scores[(long long)q * K + i] = key_score(key[i]);
+        ids[(long long)q * K + i] = (long long)key_row(key[i]) + id_offset;
+        if (i == K - 1) s_fk = key_score(key[i]);
+      } else {
+        scores[(long long)q * K + i] = -INFINITY;
+        ids[(long long)q * K + i] = -1;
+      }
+    }
   }
-  if (threadIdx.x == 0) {
-    // Rows the scan did not report have a bf16 score < thr; they are harmless iff thr <= cutoff.
+  __syncthreads();
+  if (tid == 0) {
     // flags: 1 = certified; otherwise -(reason bits): 1 list overflow, 2 fewer than K candidates,
-    // 4 tensor-core/fp32 score mismatch beyond eps, 8 prune cutoff below the scan threshold.
+    // 4 tensor-core/fp32 score mismatch beyond eps, 8 f_K does not clear the bound of the rows not rescored.
+    const float c = fmaxf(t, cutoff);                 // every row not rescored has a bf16 score < c
+    const bool unbounded = (c == -INFINITY);          // every row of the shard was rescored
     int why = 0;
     if (overflow) why |= 1;
-    if (n < K) why |= 2;
-    if (any_bad) why |= 4;
-    if (n >= K && !(t == -INFINITY) && !(cutoff >= t)) why |= 8;
+    if (m < K) why |= 2;
+    if (s_bad) why |= 4;
+    if (m >= K && !unbounded && !(s_fk >= c + my_eps)) why |= 8;
     const bool ok = why == 0;
     flags[q] = ok ? 1 : -why;
     if (!ok) atomicAdd(n_uncertified, 1);
+    // shard mode: fp32 upper bound of every row of this shard that was not rescored (global certificate)
+    if (bound_out) bound_out[q] = unbounded ? -INFINITY : c + my_eps;
   }
 }
 
 int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long long N, int D, int nq, int K,
                     long long id_offset, const float* thr, const float* eps, const unsigned int* seg_cnt,
                     const void* cand, float* scores, long long* ids, int* flags, int* n_uncertified,
-                    cudaStream_t st) {
+                    float* bound_out, cudaStream_t st) {
   TT_CHECK_ARG(pl.main_slices <= FINALIZE_MAX_SLICES, "too many catalog slices");
   const size_t smem = (size_t)pl.cand_cap * 8 + (size_t)D * 4 + 16;
   TT_CHECK_CUDA(cudaFuncSetAttribute(flat_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  flat_finalize_kernel<<<nq, 512, smem, st>>>(qn, Xn, N, D, K, id_offset, thr, eps, seg_cnt,
-                                              reinterpret_cast<const uint2*>(cand), pl.main_slices, pl.seg_cap,
-                                              pl.cand_cap, scores, ids, flags, n_uncertified);
+  flat_finalize_kernel<<<nq, FIN_THREADS, smem, st>>>(qn, Xn, N, D, K, id_offset, thr, eps, seg_cnt,
+                                                      reinterpret_cast<const uint2*>(cand), pl.main_slices, pl.seg_cap,
+                                                      pl.cand_cap, scores, ids, flags, n_uncertified, bound_out);
   TT_CHECK_LAUNCH();
   return TT_OK;
 }
@@ -246,6 +340,78 @@ topk_merge_kernel(const float* __restrict__ sg, const long long* __restrict__ ig
     const unsigned long long kk = key[i];
     scores[(long long)q * K + i] = (kk == 0ull) ? -INFINITY : key_score(kk);
     ids[(long long)q * K + i] = (kk == 0ull) ? -1 : (long long)key_row(kk);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// shard merge with the global exactness certificate: one CTA per query.
+// Every rank contributed a record {scores f32[nq,K] | ids i64[nq,K] | bound f32[nq] | flags i32[nq]} (the
+// layout ONE all-gather of the per-rank byte buffers produces).  The G lists are sorted (score desc, id
+// asc) and padded with (-inf, -1); an element's position in the merged order is its own index plus, for
+// every other list, the number of larger keys found by binary search - no sort.
+// Certificate: on shard g every row that was not rescored in fp32 scores strictly below bound_g[q]; the
+// merged top-K is exact iff its K-th score f_K >= max_g bound_g[q] (and no shard reported a candidate-list
+// overflow or a tensor-core/fp32 self-check failure).
+__global__ void __launch_bounds__(128)
+shard_merge_kernel(const unsigned char* __restrict__ gathered, size_t rank_stride, size_t off_scores, size_t off_ids,
+                   size_t off_bound, size_t off_flags, int G, int nq, int K, float* __restrict__ scores,
+                   long long* __restrict__ ids, int* __restrict__ flags, int* __restrict__ n_uncertified) {
+  extern __shared__ __align__(16) unsigned char msm[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(msm);   // [G][K]
+  __shared__ int s_valid[64];
+  __shared__ float s_fk;
+  const int q = blockIdx.x;
+  const int n = G * K;
+  if (threadIdx.x == 0) s_fk = -INFINITY;
+  if (threadIdx.x < 64) s_valid[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int g = i / K, j = i % K;
+    const unsigned char* rec = gathered + (size_t)g * rank_stride;
+    const long long id = reinterpret_cast<const long long*>(rec + off_ids)[(long long)q * K + j];
+    const float sc = reinterpret_cast<const float*>(rec + off_scores)[(long long)q * K + j];
+    key[i] = (id >= 0) ? make_key(sc, (uint32_t)id) : 0ull;
+    if (id >= 0) atomicAdd(&s_valid[g], 1);
+  }
+  __syncthreads();
+  int total = 0;
+  for (int g = 0; g < G; ++g) total += s_valid[g];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long ki = key[i];
+    if (ki == 0ull) continue;
+    const int g = i / K;
+    int rank = i % K;
+    for (int h = 0; h < G; ++h) {
+      if (h == g) continue;
+      const unsigned long long* lst = key + h * K;
+      int lo = 0, hi = s_valid[h];          // number of keys of list h that are larger than ki
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (lst[mid] > ki) lo = mid + 1; else hi = mid; }
+      rank += lo;
+    }
+    if (rank < K) {
+      scores[(long long)q * K + rank] = key_score(ki);
+      ids[(long long)q * K + rank] = (long long)key_row(ki);
+      if (rank == K - 1) s_fk = key_score(ki);
+    }
+  }
+  for (int i = total + threadIdx.x; i < K; i += blockDim.x) {
+    scores[(long long)q * K + i] = -INFINITY;
+    ids[(long long)q * K + i] = -1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int why = 0;
+    float bmax = -INFINITY;
+    for (int g = 0; g < G; ++g) {
+      const unsigned char* rec = gathered + (size_t)g * rank_stride;
+      const int f = reinterpret_cast<const int*>(rec + off_flags)[q];
+      if (f <= 0) why |= (-f) & (1 | 4);     // local "fewer than K" / local f_K checks are superseded by the global one
+      bmax = fmaxf(bmax, reinterpret_cast<const float*>(rec + off_bound)[q]);
+    }
+    if (total < K) why |= 2;
+    if (total >= K && !(bmax == -INFINITY) && !(s_fk >= bmax)) why |= 8;
+    flags[q] = why == 0 ? 1 : -why;
+    if (why) atomicAdd(n_uncertified, 1);
   }
 }
 
@@ -409,6 +575,26 @@ extern "C" __attribute__((visibility("default"))) int tt_topk_merge(const float*
   TT_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   topk_merge_kernel<<<nq, 128, smem, (cudaStream_t)stream>>>(scores_g, reinterpret_cast<const long long*>(ids_g), G,
                                                             nq, K, scores, reinterpret_cast<long long*>(ids));
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_shard_merge(const void* gathered, size_t rank_stride, size_t off_scores, size_t off_ids,
+                              size_t off_bound, size_t off_flags, int G, int nq, int K, float* scores, int64_t* ids,
+                              int32_t* flags, int32_t* n_uncertified, void* stream) {
+  TT_CHECK_ARG(gathered && scores && ids && flags && n_uncertified, "null pointer");
+  TT_CHECK_ARG(G >= 1 && G <= 64 && nq >= 0 && K >= 1, "need 1 <= G <= 64, nq >= 0, K >= 1");
+  TT_CHECK_ARG((long long)G * K <= FINALIZE_MAX_CAND, "G*K exceeds 16384");
+  TT_CHECK_ARG(off_scores % 4 == 0 && off_ids % 8 == 0 && off_bound % 4 == 0 && off_flags % 4 == 0 && rank_stride % 8 == 0,
+               "misaligned record layout");
+  cudaStream_t st = (cudaStream_t)stream;
+  TT_CHECK_CUDA(cudaMemsetAsync(n_uncertified, 0, sizeof(int32_t), st));
+  if (nq == 0) return TT_OK;
+  const size_t smem = (size_t)G * K * 8;
+  TT_CHECK_CUDA(cudaFuncSetAttribute(shard_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  shard_merge_kernel<<<nq, 128, smem, st>>>(reinterpret_cast<const unsigned char*>(gathered), rank_stride, off_scores,
+                                            off_ids, off_bound, off_flags, G, nq, K, scores,
+                                            reinterpret_cast<long long*>(ids), flags, n_uncertified);
   TT_CHECK_LAUNCH();
   return TT_OK;
 }

@@ -1,16 +1,22 @@
 """Catalog sharding across GPUs (north_star (3); the reference has no multi-device path).
 
-One process per GPU.  Rank r owns the contiguous catalog rows [lo_r, hi_r); every rank searches
-its shard for the replicated query batch, the per-rank (scores, ids) [nq,K] lists are exchanged
-with ONE all-gather (NCCL over NVLink/NVSwitch), and a merge kernel (tt_topk_merge) reduces the G
-sorted lists to the global top-K on every rank.  ids are global row numbers (local row + lo_r).
+One process per GPU.  Rank r owns the contiguous catalog rows [lo_r, hi_r); every rank searches its
+shard for the replicated query batch and writes its result straight into one byte record
 
-The local-search and merge steps are injectable so that the exchange logic is testable on CPU with
-the gloo backend (tests/test_sharded_gloo.py).
+    { scores f32[nq,K] | ids i64[nq,K] | bound f32[nq] | flags i32[nq] }
+
+(ids are global row numbers; lists shorter than K are padded with score -inf / id -1).  ONE
+all-gather of the records (NCCL over NVLink/NVSwitch) and a merge kernel (tt_shard_merge) produce the
+global top-K on every rank together with a *global* exactness certificate: the merged K-th score must
+clear, on every shard, the bound of the rows that shard did not rescore in fp32.  Queries that fail it
+(rare) are re-run through the always-exact fp32 path on every shard and merged again.
+
+The local search and the merge are injectable so that the pack / exchange / fallback logic is testable
+on CPU with the gloo backend (tests/test_sharded_gloo.py).
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+from typing import Callable, NamedTuple, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -26,43 +32,101 @@ def shard_bounds(n_total: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, hi
 
 
-def gather_and_merge(scores: torch.Tensor, ids: torch.Tensor, merge: Callable, group=None):
-    """All-gathers per-rank [nq,K] lists into [G,nq,K] and merges them."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if world == 1:
-        return scores, ids
-    nq, k = scores.shape
-    sg = torch.empty((world, nq, k), device=scores.device, dtype=scores.dtype)
-    ig = torch.empty((world, nq, k), device=ids.device, dtype=ids.dtype)
-    dist.all_gather_into_tensor(sg.view(world * nq, k), scores.contiguous(), group=group)
-    dist.all_gather_into_tensor(ig.view(world * nq, k), ids.contiguous(), group=group)
-    return merge(sg, ig)
+class RecordLayout(NamedTuple):
+    """Byte offsets of one rank's record (every field 16-byte aligned)."""
+    off_scores: int
+    off_ids: int
+    off_bound: int
+    off_flags: int
+    nbytes: int
+
+
+def record_layout(nq: int, k: int) -> RecordLayout:
+    def up(x):
+        return (x + 15) // 16 * 16
+    o_scores = 0
+    o_ids = up(o_scores + nq * k * 4)
+    o_bound = up(o_ids + nq * k * 8)
+    o_flags = up(o_bound + nq * 4)
+    return RecordLayout(o_scores, o_ids, o_bound, o_flags, up(o_flags + nq * 4))
+
+
+def record_views(buf: torch.Tensor, lay: RecordLayout, nq: int, k: int):
+    """Typed views (scores, ids, bound, flags) into a uint8 record (or a [G, nbytes] stack of records)."""
+    lead = buf.shape[:-1]
+
+    def field(off, n, dtype, shape):
+        size = torch.empty((), dtype=dtype).element_size()
+        return buf[..., off:off + n * size].view(dtype).view(*lead, *shape)
+    return (field(lay.off_scores, nq * k, torch.float32, (nq, k)), field(lay.off_ids, nq * k, torch.int64, (nq, k)),
+            field(lay.off_bound, nq, torch.float32, (nq,)), field(lay.off_flags, nq, torch.int32, (nq,)))
+
+
+def _merge_cuda(gathered: torch.Tensor, lay: RecordLayout, nq: int, k: int):
+    from . import ops
+    return ops.shard_merge(gathered, lay.off_scores, lay.off_ids, lay.off_bound, lay.off_flags, nq, k)
 
 
 class ShardedFlatIPIndex:
-    """A FlatIPIndex per rank over its row block + all-gather/merge search."""
+    """A FlatIPIndex per rank over its row block + all-gather/merge search.
+
+    `local_index` provides `ntotal`, `search_shard_into(q, k_local, scores, ids, bound, flags)` and
+    `search_exact_into(q, k_local, scores, ids, qsel)`, both writing the first k_local columns of the
+    [nq,k] record views (see FlatIPIndex).
+    `merge(gathered[G,nbytes] uint8, layout, nq, k) -> (scores, ids, flags, n_uncertified)`.
+    """
 
     def __init__(self, local_index, n_total: int, group=None, merge: Optional[Callable] = None):
         self.local = local_index
         self.n_total = int(n_total)
         self.group = group
-        if merge is None:
-            from . import ops
-            merge = ops.topk_merge
-        self._merge = merge
+        self._merge = merge if merge is not None else _merge_cuda
+        self._bufs = {}
 
     @property
     def ntotal(self) -> int:
         return self.n_total
 
+    def _buffers(self, nq: int, k: int, device, world: int):
+        key = (nq, k, world)
+        b = self._bufs.get(key)
+        if b is None:
+            lay = record_layout(nq, k)
+            rec = torch.zeros(lay.nbytes, dtype=torch.uint8, device=device)
+            gathered = torch.zeros((world, lay.nbytes), dtype=torch.uint8, device=device)
+            if len(self._bufs) > 8:
+                self._bufs.clear()
+            b = self._bufs[key] = (lay, rec, gathered)
+        return b
+
+    def _exchange(self, rec: torch.Tensor, gathered: torch.Tensor, world: int):
+        if world == 1:
+            gathered[0].copy_(rec)
+        else:
+            dist.all_gather_into_tensor(gathered.view(-1), rec, group=self.group)
+
     def search_device(self, q: torch.Tensor, k: int):
         """q replicated on every rank -> global (scores, ids) [nq,k] on every rank, and the number of
-        local queries that needed the exact re-run."""
+        queries that failed the global certificate and were re-run through the exact path."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        nq = q.shape[0]
+        lay, rec, gathered = self._buffers(nq, k, q.device, world)
+        scores, ids, bound, flags = record_views(rec, lay, nq, k)
         k_local = min(k, self.local.ntotal)
-        scores, ids, n_bad = self.local.search_checked_device(q, k_local)
         if k_local < k:   # shard smaller than k: pad so every rank contributes [nq,k]
-            pad_s = torch.full((q.shape[0], k - k_local), float("-inf"), device=scores.device)
-            pad_i = torch.full((q.shape[0], k - k_local), -1, device=ids.device, dtype=ids.dtype)
-            scores, ids = torch.cat([scores, pad_s], 1), torch.cat([ids, pad_i], 1)
-        s, i = gather_and_merge(scores, ids, self._merge, self.group)
+            scores.fill_(float("-inf"))
+            ids.fill_(-1)
+        self.local.search_shard_into(q, k_local, scores, ids, bound, flags)
+        self._exchange(rec, gathered, world)
+        s, i, fl, n_unc = self._merge(gathered, lay, nq, k)
+        n_bad = int(n_unc)                       # identical on every rank: all ranks merged the same records
+        if n_bad:
+            qsel = torch.nonzero(fl != 1).flatten().to(torch.int32)
+            self.local.search_exact_into(q, k_local, scores, ids, qsel)
+            bound[qsel.long()] = float("-inf")
+            flags[qsel.long()] = 1
+            self._exchange(rec, gathered, world)
+            s, i, fl, n_unc2 = self._merge(gathered, lay, nq, k)
+            if int(n_unc2):
+                raise RuntimeError("sharded search: queries still uncertified after the exact re-run")
         return s, i, n_bad

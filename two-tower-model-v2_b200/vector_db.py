@@ -201,6 +201,37 @@ class FlatIPIndex:
                 self._exact_ws.numel(), ops._stream()), "tt_flat_search_exact")
         return scores, ids
 
+    def search_shard_into(self, q: torch.Tensor, k: int, scores: torch.Tensor, ids: torch.Tensor,
+                          bound: torch.Tensor, flags: torch.Tensor) -> None:
+        """Shard-local search for ShardedFlatIPIndex (tt_flat_search_shard): fills the caller's record views.
+        scores/ids are [nq, k_record] with k_record >= k; only the first k columns of each row are written."""
+        q = ops._f32c(q, "queries")
+        nq = q.shape[0]
+        direct = scores.shape[1] == k and scores.is_contiguous() and ids.is_contiguous()
+        s_out = scores if direct else torch.empty((nq, k), device=self.device, dtype=torch.float32)
+        i_out = ids if direct else torch.empty((nq, k), device=self.device, dtype=torch.int64)
+        nunc = torch.empty((1,), device=self.device, dtype=torch.int32)
+        ws = self._workspace(max(nq, 1), k)
+        with torch.cuda.device(self.device):
+            _native.check(_native.load().tt_flat_search_shard(
+                q.data_ptr(), nq, self.xn.data_ptr(), self.xh.data_ptr(), self.stats.data_ptr(), self.ntotal, self.d,
+                k, self.id_offset, s_out.data_ptr(), i_out.data_ptr(), flags.data_ptr(), nunc.data_ptr(),
+                bound.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream()), "tt_flat_search_shard")
+        if not direct:
+            scores[:, :k].copy_(s_out)
+            ids[:, :k].copy_(i_out)
+
+    def search_exact_into(self, q: torch.Tensor, k: int, scores: torch.Tensor, ids: torch.Tensor,
+                          qsel: torch.Tensor) -> None:
+        """Exact fp32 re-run of the query rows `qsel`, written into [nq, k_record] record views."""
+        if scores.shape[1] == k and scores.is_contiguous() and ids.is_contiguous():
+            self.search_exact_device(q, k, scores, ids, qsel)
+            return
+        s_tmp, i_tmp = self.search_exact_device(q, k)
+        rows = qsel.long()
+        scores[rows, :k] = s_tmp[rows]
+        ids[rows, :k] = i_tmp[rows]
+
     def scan_scores_device(self, q: torch.Tensor) -> torch.Tensor:
         """Diagnostic: dense bf16 tensor-core scores [nq, N] exactly as the scan epilogue sees them
         (tt_flat_scan_scores; small catalogs only).  Rows never reported by the kernel read NaN."""
