@@ -52,6 +52,8 @@ constexpr int UMMA_K = 16;
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;                  // 2 accumulator buffers x 256 fp32 columns
 constexpr int CHUNKS = BLOCK_N / 32;
+constexpr int BAR_BYTES = 256;                  // mbarriers + TMEM base pointer
+constexpr int SCRATCH_BYTES = 4 * 256;          // one 64-value row per epilogue warp (candidate extraction)
 
 struct ScanParams {
   long long N;            // catalog rows
@@ -125,20 +127,6 @@ __device__ __noinline__ float max_columns(uint32_t taddr, int ncols) {
   return m;
 }
 
-// Append every register-resident column that reaches the threshold.  Predicated straight-line code:
-// all lanes run it, each on its own (query, slice) segment.  On overflow the last slot is overwritten
-// and the count keeps growing, which finalize reports as "overflow" (exact re-run of that query).
-__device__ __forceinline__ void append_regs(const uint32_t (&v)[32], float thr, uint32_t row_base, uint2* seg,
-                                            unsigned int& cnt, unsigned int last) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (__uint_as_float(v[j]) >= thr) {
-      seg[min(cnt, last)] = make_uint2(v[j], row_base + (uint32_t)j);
-      ++cnt;
-    }
-  }
-}
-
 template <int BLOCK_M, bool SAMPLE, bool PAIR>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
@@ -159,6 +147,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* tmem_full_bar = a_full_bar + 1;        // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint32_t* scratch_base = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);   // 4 x 256 B
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -281,7 +270,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (!SAMPLE && valid) thr = __ldg(p.thr + q);
     uint2* my_cand = SAMPLE ? nullptr : (p.cand + ((size_t)(valid ? q : 0) * p.nslices + slice) * p.seg_cap);
     unsigned int my_cnt = 0;
-    const unsigned int seg_last = (unsigned int)(p.seg_cap > 0 ? p.seg_cap - 1 : 0);
+    uint32_t* scratch = scratch_base + (warp - 4) * 64;
 
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
@@ -307,17 +296,38 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (SAMPLE) {
             if (p.sample_tile_max) tile_max = fmaxf(tile_max, fmaxf(m0, m1));
             else if (valid) *reinterpret_cast<float2*>(sample_row + c) = make_float2(m0, m1);
-          } else if (__any_sync(0xffffffffu, fmaxf(m0, m1) >= thr)) {
-            // rare (a few % of the steps): some column qualifies for some lane.  The values are still in
-            // registers: one predicated compare/append per column, shared by both halves through a rolled
-            // 2-iteration loop so the code stays small.
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-              uint32_t s[32];
+          } else {
+            // Lanes (queries) with a qualifying column among these 64.  Hits are sparse - a handful per
+            // tile for the whole warp - so they are extracted cooperatively: the hit lane spills its 64
+            // values to a 256-byte scratch row, the warp re-reads them one column per lane, and the
+            // qualifying (score, row) pairs are appended to that query's segment with ballot-prefix
+            // positions (coalesced 8-byte stores).  Cost is per hit, not per column.
+            unsigned int hitmask = __ballot_sync(0xffffffffu, fmaxf(m0, m1) >= thr);
+            while (hitmask) {
+              const int src = __ffs(hitmask) - 1;
+              hitmask &= hitmask - 1;
+              if (lane == src) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) s[j] = h ? v1[j] : v0[j];
-              if (__any_sync(0xffffffffu, (h ? m1 : m0) >= thr))
-                append_regs(s, thr, (uint32_t)row0 + (uint32_t)((c + h) * 32), my_cand, my_cnt, seg_last);
+                for (int j = 0; j < 32; j += 4) {
+                  *reinterpret_cast<uint4*>(scratch + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+                  *reinterpret_cast<uint4*>(scratch + 32 + j) = make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
+                }
+              }
+              __syncwarp();
+              const float thr_s = __shfl_sync(0xffffffffu, thr, src);
+              const unsigned int cnt_s = __shfl_sync(0xffffffffu, my_cnt, src);
+              const int q_s = __shfl_sync(0xffffffffu, q, src);
+              const uint32_t x0 = scratch[lane], x1 = scratch[32 + lane];
+              const bool h0 = __uint_as_float(x0) >= thr_s, h1 = __uint_as_float(x1) >= thr_s;
+              const unsigned int b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
+              const unsigned int lt = (1u << lane) - 1u;
+              const unsigned int p0 = cnt_s + __popc(b0 & lt), p1 = cnt_s + __popc(b0) + __popc(b1 & lt);
+              uint2* seg = p.cand + ((size_t)q_s * p.nslices + slice) * p.seg_cap;
+              const uint32_t rbase = (uint32_t)row0 + (uint32_t)(c * 32 + lane);
+              if (h0 && p0 < (unsigned int)p.seg_cap) seg[p0] = make_uint2(x0, rbase);
+              if (h1 && p1 < (unsigned int)p.seg_cap) seg[p1] = make_uint2(x1, rbase + 32u);
+              if (lane == src) my_cnt += __popc(b0) + __popc(b1);
+              __syncwarp();
             }
           }
         };
@@ -558,7 +568,7 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   pl.num_kb = pl.Dp / BLOCK_K;
   const int sms = num_sms();
   // A (queries) stays resident: M=128 per CTA while it leaves room for >= 3 full-tile B stages, else M=64.
-  const int budget = 227 * 1024 - 2048;   // barriers + alignment slack
+  const int budget = 227 * 1024 - 1024 /*align*/ - BAR_BYTES - SCRATCH_BYTES;
   pl.block_m = 128;
   if (budget - pl.num_kb * 128 * 128 < 3 * (BLOCK_N * BLOCK_K * 2)) pl.block_m = 64;
   pl.pair = (pl.block_m == 128) && (nq > 128) && (sms >= 2);
@@ -567,7 +577,7 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   pl.num_stages = (budget - a_bytes) / b_stage;
   if (pl.num_stages > MAX_STAGES) pl.num_stages = MAX_STAGES;
   pl.supported = pl.num_stages >= 2;
-  pl.smem_bytes = (size_t)a_bytes + (size_t)pl.num_stages * b_stage + 1024 /*align*/ + 256 /*barriers*/;
+  pl.smem_bytes = (size_t)a_bytes + (size_t)pl.num_stages * b_stage + 1024 /*align*/ + BAR_BYTES + SCRATCH_BYTES;
   pl.nqb = (nq + pl.block_m - 1) / pl.block_m;
   if (pl.pair) pl.nqb = (pl.nqb + 1) / 2 * 2;
   pl.nq_pad = pl.nqb * pl.block_m;
