@@ -166,6 +166,28 @@ int tt_flat_search_shard(const float* q, int nq,
                          int K, int64_t id_offset,
                          float* scores, int64_t* ids, int32_t* flags, int32_t* n_uncertified, float* bound,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* One threshold for the whole sharded catalog (the fast sharded path; both calls use the SAME workspace):
+ *   tt_flat_shard_plan_ok   host-only, 1 if this path applies to (N_local, N_total, D, nq, K) - a function of
+ *                           N_total, D, nq, K and of N_local >= K only, so every rank decides alike when
+ *                           called with its smallest shard; otherwise use tt_flat_search_shard.
+ *   tt_flat_shard_sample    renormalises the queries, samples this shard's tiles at the stride a single device
+ *                           would use for N_total rows and writes each query's TT_SHARD_TOPR largest sampled
+ *                           scores, descending, -inf padded: topr f32 [nq, TT_SHARD_TOPR].
+ *   (all-gather the lists: topr_g f32 [G, nq, TT_SHARD_TOPR])
+ *   tt_flat_shard_search    threshold = planned rank among the union of the G lists (identical on every rank),
+ *                           main scan, finalize; outputs as tt_flat_search_shard.  The threshold only decides
+ *                           how many candidates are rescored; exactness rests on the certificate of
+ *                           tt_shard_merge. */
+#define TT_SHARD_TOPR 32
+int tt_flat_shard_plan_ok(int64_t N_local, int64_t N_total, int D, int nq, int K);
+size_t tt_flat_shard_workspace_bytes(int64_t N_local, int64_t N_total, int D, int nq, int K);
+int tt_flat_shard_sample(const float* q, int nq, const void* Xh, const float* stats,
+                         int64_t N_local, int64_t N_total, int D, int K, float* topr,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int tt_flat_shard_search(int nq, const float* Xn, const void* Xh, int64_t N_local, int64_t N_total, int D,
+                         int K, int64_t id_offset, const float* topr_g, int G,
+                         float* scores, int64_t* ids, int32_t* flags, int32_t* n_uncertified, float* bound,
+                         void* workspace, size_t workspace_bytes, void* stream);
 int tt_shard_merge(const void* gathered, size_t rank_stride, size_t off_scores, size_t off_ids,
                    size_t off_bound, size_t off_flags, int G, int nq, int K,
                    float* scores, int64_t* ids, int32_t* flags, int32_t* n_uncertified, void* stream);

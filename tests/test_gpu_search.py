@@ -262,3 +262,40 @@ def test_shard_merge_global_certificate_rejects_and_recovers():
     s, i, flags, nunc = ops.shard_merge(gathered, lay.off_scores, lay.off_ids, lay.off_bound, lay.off_flags, nq, k)
     assert flags.cpu().tolist() == [-8, 1, -1, -4, 1, 1, 1, 1]
     assert int(nunc.item()) == 3
+
+
+@pytest.mark.parametrize("N,D,nq,k,G", [(3_000_000, 64, 200, 100, 4), (2_200_000, 384, 33, 10, 8)])
+def test_shard_global_threshold_path(N, D, nq, k, G):
+    """tt_flat_shard_sample / tt_flat_shard_search on G shards of one device: one threshold from the gathered
+    sample, ~target/G candidates per shard, merged result identical to the single-index search."""
+    import two_tower_model_v2_b200 as pkg
+    from two_tower_model_v2_b200 import _native, ops
+    from two_tower_model_v2_b200.sharded import record_layout, record_views
+    g = torch.Generator(device="cuda").manual_seed(77)
+    x = torch.randn((N, D), device=dev(), generator=g)
+    q = torch.randn((nq, D), device=dev(), generator=g)
+    full = pkg.FlatIPIndex.adopt(x.clone())
+    fs, fi, fbad = full.search_checked_device(q, k)
+    shards = []
+    for r in range(G):
+        lo, hi = pkg.shard_bounds(N, G, r)
+        idx = pkg.FlatIPIndex.adopt(x[lo:hi].clone())
+        idx.id_offset = lo
+        shards.append(idx)
+    n_min = min(s.ntotal for s in shards)
+    assert shards[0].shard_plan_ok(N, nq, k, n_min)
+    topr_g = torch.empty((G, nq, _native.TT_SHARD_TOPR), device=dev())
+    for r, idx in enumerate(shards):
+        idx.shard_sample(q, k, N, topr_g[r])
+    assert (topr_g[:, :, 1:] <= topr_g[:, :, :-1]).all()           # descending lists, -inf padded
+    lay = record_layout(nq, k)
+    gathered = torch.zeros((G, lay.nbytes), dtype=torch.uint8, device=dev())
+    for r, idx in enumerate(shards):
+        s, i, b, f = record_views(gathered[r], lay, nq, k)
+        idx.shard_search_into(nq, k, N, topr_g, s, i, b, f)
+    s, i, flags, nunc = ops.shard_merge(gathered, lay.off_scores, lay.off_ids, lay.off_bound, lay.off_flags, nq, k)
+    assert int(nunc.item()) == 0
+    assert torch.equal(i, fi) and torch.equal(s, fs)
+    # every shard used the same threshold: the bounds differ only through the local prune cutoff
+    _, _, bg, _ = record_views(gathered, lay, nq, k)
+    assert torch.isfinite(bg).all()

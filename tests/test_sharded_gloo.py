@@ -43,6 +43,27 @@ class _LocalOracleIndex:
         ids[rows, :k] = torch.from_numpy(i + self.id_offset)
 
 
+class _GlobalThresholdOracleIndex(_LocalOracleIndex):
+    """Adds the two-phase contract (shard_sample -> all-gather -> shard_search_into): the stand-in publishes
+    its rank in the list and checks that it sees every rank's list before searching."""
+
+    def __init__(self, xn_shard, id_offset, rank, world):
+        super().__init__(xn_shard, id_offset)
+        self.rank, self.world, self.q = rank, world, None
+
+    def shard_plan_ok(self, n_total, nq, k, n_local_min):
+        return n_local_min >= k
+
+    def shard_sample(self, q, k, n_total, topr):
+        self.q = q
+        topr.fill_(float(self.rank))
+
+    def shard_search_into(self, nq, k, n_total, topr_g, scores, ids, bound, flags):
+        assert topr_g.shape[0] == self.world
+        assert [float(topr_g[g, 0, 0]) for g in range(self.world)] == [float(g) for g in range(self.world)]
+        self.search_shard_into(self.q, k, scores, ids, bound, flags)
+
+
 def _merge_oracle(gathered, lay, nq, K):
     """numpy restatement of tt_shard_merge (merge + global certificate)."""
     from two_tower_model_v2_b200.sharded import record_views
@@ -85,7 +106,7 @@ class _FlagOnceMerge:
         return s, i, f, n
 
 
-def _worker(rank, world, port, N, D, k, out_dir, flag_once=False):
+def _worker(rank, world, port, N, D, k, out_dir, flag_once=False, two_phase=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import two_tower_model_v2_b200 as pkg
@@ -93,7 +114,7 @@ def _worker(rank, world, port, N, D, k, out_dir, flag_once=False):
     xn = fo.normalize_rows(rng.standard_normal((N, D)).astype(np.float32))
     q = rng.standard_normal((6, D)).astype(np.float32)
     lo, hi = pkg.shard_bounds(N, world, rank)
-    local = _LocalOracleIndex(xn[lo:hi], lo)
+    local = _GlobalThresholdOracleIndex(xn[lo:hi], lo, rank, world) if two_phase else _LocalOracleIndex(xn[lo:hi], lo)
     merge = _FlagOnceMerge() if flag_once else _merge_oracle
     sharded = pkg.ShardedFlatIPIndex(local, N, merge=merge)
     s, i, n_bad = sharded.search_device(torch.from_numpy(q), k)
@@ -148,3 +169,16 @@ def test_record_layout_alignment():
         assert s.shape == (2, nq, k) and i.shape == (2, nq, k) and b.shape == (2, nq) and f.shape == (2, nq)
         i[1, nq - 1, k - 1] = -1
         assert buf[1, lay.off_ids + (nq * k - 1) * 8:lay.off_ids + nq * k * 8].tolist() == [255] * 8
+
+
+def test_two_phase_global_threshold_exchange(tmp_path):
+    N, D, k, world = 800, 16, 10, 2
+    mp.spawn(_worker, args=(world, _free_port(), N, D, k, str(tmp_path), True, True), nprocs=world, join=True)
+    rng = np.random.default_rng(0)
+    xn = fo.normalize_rows(rng.standard_normal((N, D)).astype(np.float32))
+    q = rng.standard_normal((6, D)).astype(np.float32)
+    rs, ri = fo.search(xn, fo.normalize_rows(q), k)
+    for r in range(world):
+        g = np.load(tmp_path / f"r{r}.npz")
+        assert int(g["n_bad"]) == 1
+        assert np.array_equal(g["i"], ri) and np.allclose(g["s"], rs, atol=1e-6)

@@ -4,13 +4,13 @@ NS=${1:-2}
 mkdir -p gpurun_out
 O=gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
-timeout 600 python -m pytest tests/test_gpu_search.py -q -x -k "shard or merge" 2>&1 | tail -5
+timeout 900 python -m pytest tests -q -x -m gpu 2>&1 | tail -5
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-secondary > $O/scale_n1.log 2>&1
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 --no-secondary > $O/scale_n1.log 2>&1
 for N in $NS; do
   timeout 600 $TR --nproc-per-node $N --master-port 2951$N tools/check_sharded.py 1000000 384 300 100 2>&1 | grep -v "^W\|^\*\*\*" | tail -3
   timeout 600 $TR --nproc-per-node $N --master-port 2952$N tools/check_sharded.py 3000 64 50 1000 2>&1 | grep -v "^W\|^\*\*\*" | tail -3
-  timeout 900 $TR --nproc-per-node $N --master-port 2953$N bench.py --gpus $N --steps 10 --warmup 3 > $O/scale_n$N.log 2>$O/scale_n$N.err
+  timeout 900 $TR --nproc-per-node $N --master-port 2953$N bench.py --gpus $N --steps 40 --warmup 3 > $O/scale_n$N.log 2>$O/scale_n$N.err
 done
 python - <<PY
 import json

@@ -149,6 +149,65 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_search_shard(const
 }
 
 // ------------------------------------------------------------------------------------------
+// Sharded catalogs with ONE threshold for the whole catalog (include/tt_b200.h).
+extern "C" __attribute__((visibility("default"))) int tt_flat_shard_plan_ok(int64_t N_local, int64_t N_total, int D, int nq, int K) {
+  if (N_local < 1 || N_total < N_local || D < 1 || nq < 1 || K < 1) return 0;
+  bool ok = false;
+  (void)make_shard_plan(N_local, N_total, D, nq, K, &ok);
+  return ok ? 1 : 0;
+}
+
+extern "C" __attribute__((visibility("default"))) size_t tt_flat_shard_workspace_bytes(int64_t N_local, int64_t N_total, int D, int nq, int K) {
+  if (N_local < 1 || N_total < N_local || D < 1 || nq < 1 || K < 1) return 0;
+  bool ok = false;
+  const ScanPlan pl = make_shard_plan(N_local, N_total, D, nq, K, &ok);
+  return ok ? search_ws_layout(pl, D, nq).total : 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_flat_shard_sample(const float* q, int nq, const void* Xh, const float* stats, int64_t N_local,
+                                    int64_t N_total, int D, int K, float* topr, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  TT_CHECK_ARG(q && Xh && stats && topr && workspace, "null pointer");
+  TT_CHECK_ARG(nq >= 1 && N_local >= 1 && N_local < (1LL << 31) && N_total >= N_local && D >= 1 && K >= 1, "bad sizes");
+  TT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  bool ok = false;
+  const ScanPlan pl = make_shard_plan(N_local, N_total, D, nq, K, &ok);
+  if (!ok) { set_error("tt_flat_shard_sample: no global-threshold plan for these sizes (use tt_flat_search_shard)"); return TT_ERR_UNSUPPORTED; }
+  const SearchWs w = search_ws_layout(pl, D, nq);
+  if (workspace_bytes < w.total) { set_error("tt_flat_shard_sample: workspace too small"); return TT_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  if (int e = launch_prep_queries(q, nq, pl.nq_pad, D, pl.Dp, stats, reinterpret_cast<float*>(ws + w.qn), ws + w.qh,
+                                  reinterpret_cast<float*>(ws + w.eps), st)) return e;
+  return launch_sample(pl, ws + w.qh, Xh, N_local, nq, nullptr, topr, reinterpret_cast<float*>(ws + w.sample), st);
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_flat_shard_search(int nq, const float* Xn, const void* Xh, int64_t N_local, int64_t N_total, int D,
+                                    int K, int64_t id_offset, const float* topr_g, int G, float* scores, int64_t* ids,
+                                    int32_t* flags, int32_t* n_uncertified, float* bound, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  TT_CHECK_ARG(Xn && Xh && topr_g && scores && ids && flags && n_uncertified && bound && workspace, "null pointer");
+  TT_CHECK_ARG(nq >= 1 && G >= 1 && G <= 64 && N_local >= 1 && N_local < (1LL << 31) && N_total >= N_local, "bad sizes");
+  TT_CHECK_ARG(K >= 1 && K <= N_local && K <= TT_FLAT_MAX_K, "need 1 <= K <= min(N_local, TT_FLAT_MAX_K)");
+  bool ok = false;
+  const ScanPlan pl = make_shard_plan(N_local, N_total, D, nq, K, &ok);
+  if (!ok) { set_error("tt_flat_shard_search: no global-threshold plan for these sizes"); return TT_ERR_UNSUPPORTED; }
+  const SearchWs w = search_ws_layout(pl, D, nq);
+  if (workspace_bytes < w.total) { set_error("tt_flat_shard_search: workspace too small"); return TT_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  TT_CHECK_CUDA(cudaMemsetAsync(n_uncertified, 0, sizeof(int32_t), st));
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  float* qn = reinterpret_cast<float*>(ws + w.qn);
+  float* eps = reinterpret_cast<float*>(ws + w.eps);
+  float* thr = reinterpret_cast<float*>(ws + w.thr);
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(ws + w.cnt);
+  if (int e = launch_select_gathered(topr_g, G, nq, pl.sample_rank, thr, st)) return e;
+  if (int e = launch_main_scan(pl, ws + w.qh, Xh, N_local, nq, thr, cnt, ws + w.cand, st)) return e;
+  return launch_finalize(pl, qn, Xn, N_local, D, nq, K, id_offset, thr, eps, cnt, ws + w.cand, scores,
+                         reinterpret_cast<long long*>(ids), flags, n_uncertified, bound, st);
+}
+
+// ------------------------------------------------------------------------------------------
 // Diagnostic: dense bf16 tensor-core scores of a small catalog (parity tests of the scan itself).
 namespace tt {
 __global__ void scatter_scores_kernel(const unsigned int* __restrict__ seg_cnt, const uint2* __restrict__ cand,

@@ -7,6 +7,7 @@
 namespace tt {
 
 constexpr int SAMPLE_MAX_SLOTS = 4096;      // sampled tiles per query (8 chunk maxima each are staged in smem)
+constexpr int SHARD_TOPR = 32;              // sampled maxima per query a shard contributes to the global threshold
 constexpr int FINALIZE_MAX_SLICES = 1024;   // catalog slices per query the finalize kernel gathers
 constexpr int FINALIZE_MAX_CAND = 16384;   // candidates per query the finalize kernel can sort (128 KiB smem)
 
@@ -36,6 +37,14 @@ int launch_prep_queries(const float* q, int nq, int nq_pad, int D, int Dp, const
 // sample pass (if plan.use_threshold) + threshold selection + main scan
 int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq,
                 float* thr, unsigned int* seg_cnt, void* cand, float* sample_buf, cudaStream_t st);
+
+// the pieces launch_scan is made of (the sharded path runs them with an exchange in between)
+ScanPlan make_shard_plan(long long N_local, long long N_total, int D, int nq, int K, bool* global_ok);
+int launch_sample(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr, float* topr,
+                  float* sample_buf, cudaStream_t st);
+int launch_select_gathered(const float* topr_g, int G, int nq, int r, float* thr, cudaStream_t st);
+int launch_main_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr,
+                     unsigned int* seg_cnt, void* cand, cudaStream_t st);
 
 // fp32 rescoring of every candidate, exact sort, certificate
 int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long long N, int D, int nq, int K,

@@ -461,7 +461,8 @@ select_threshold_kernel(const float* __restrict__ sample, int n, int npad, int r
 // values; only the winning lane rescans).  No block-wide barrier inside the rounds.
 constexpr int SEL_WQ = 8;   // queries (warps) per CTA
 __global__ void __launch_bounds__(SEL_WQ * 32)
-select_threshold_tile_kernel(const float* __restrict__ sample, int slots, int ld, int nq, int r, float* __restrict__ thr) {
+select_threshold_tile_kernel(const float* __restrict__ sample, int slots, int ld, int nq, int r, float* __restrict__ thr,
+                             float* __restrict__ topr, int topr_ld) {
   extern __shared__ float sv[];   // [SEL_WQ][slots]
   const int q0 = blockIdx.x * SEL_WQ;
   for (int e = threadIdx.x; e < slots * SEL_WQ; e += blockDim.x) {
@@ -490,10 +491,56 @@ select_threshold_tile_kernel(const float* __restrict__ sample, int slots, int ld
       if (ob > wb || (ob == wb && oi > wi)) { wb = ob; wi = oi; }
     }
     result = (wi >= 0) ? wb : -INFINITY;
+    if (topr && lane == 0 && round < topr_ld) topr[(size_t)q * topr_ld + round] = result;
     if (wi >= 0 && wi == bi) {      // this lane owns the winner: drop it and rescan its own values
       v[wi] = -INFINITY;
       best = -INFINITY; bi = -1;
       for (int i = lane; i < slots; i += 32) {
+        const float x = v[i];
+        if (x > best) { best = x; bi = i; }
+      }
+    }
+    __syncwarp();
+  }
+  if (thr && lane == 0) thr[q] = result;
+  if (topr) for (int i = r + lane; i < topr_ld; i += 32) topr[(size_t)q * topr_ld + i] = -INFINITY;
+}
+
+// Sharded catalogs: thr[q] = r-th largest of the union of every rank's top-r sampled tile maxima
+// (gathered f32 [G, nq, SHARD_TOPR], the layout an all-gather of the per-rank lists produces): the same
+// threshold on every rank, estimated from a sample of the WHOLE catalog.  One warp per query.
+__global__ void __launch_bounds__(SEL_WQ * 32)
+select_threshold_gathered_kernel(const float* __restrict__ gathered, int G, int nq, int r, float* __restrict__ thr) {
+  extern __shared__ float sv[];   // [SEL_WQ][G * SHARD_TOPR]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * SEL_WQ + warp;
+  if (q >= nq) return;
+  const int n = G * SHARD_TOPR;
+  float* v = sv + warp * n;
+  float best = -INFINITY;
+  int bi = -1;
+  for (int i = lane; i < n; i += 32) {
+    const int g = i / SHARD_TOPR, j = i % SHARD_TOPR;
+    const float x = gathered[((size_t)g * nq + q) * SHARD_TOPR + j];
+    v[i] = x;
+    if (x > best) { best = x; bi = i; }
+  }
+  __syncwarp();
+  float result = -INFINITY;
+  for (int round = 0; round < r; ++round) {
+    float wb = best;
+    int wi = bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, wb, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (ob > wb || (ob == wb && oi > wi)) { wb = ob; wi = oi; }
+    }
+    result = (wi >= 0) ? wb : -INFINITY;
+    if (wi >= 0 && wi == bi) {
+      v[wi] = -INFINITY;
+      best = -INFINITY; bi = -1;
+      for (int i = lane; i < n; i += 32) {
         const float x = v[i];
         if (x > best) { best = x; bi = i; }
       }
@@ -699,45 +746,106 @@ static int launch_scan_mode(const ScanPlan& pl, const CUtensorMap& tq, const CUt
   return launch_scan_t<64, SAMPLE, false>(tq, tx, sp, units, pl.smem_bytes, st);
 }
 
-int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq,
-                float* thr, unsigned int* seg_cnt, void* cand, float* sample_buf, cudaStream_t st) {
+static int make_scan_params(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr,
+                            unsigned int* seg_cnt, void* cand, float* sample_buf, CUtensorMap* tq, CUtensorMap* tx,
+                            ScanParams* sp) {
+  if (int e = make_tmap_bf16(tq, qh, pl.nq_pad, pl.Dp, pl.block_m)) return e;
+  if (int e = make_tmap_bf16(tx, Xh, N, pl.Dp, pl.pair ? BLOCK_N / 2 : BLOCK_N)) return e;
+  *sp = ScanParams{};
+  sp->N = N; sp->nq = nq; sp->num_kb = pl.num_kb; sp->num_stages = pl.num_stages; sp->nqu = pl.nqu;
+  sp->thr = thr; sp->seg_cnt = seg_cnt; sp->cand = reinterpret_cast<uint2*>(cand); sp->seg_cap = pl.seg_cap;
+  sp->sample_out = sample_buf;
+  sp->sample_tile_max = pl.sample_tile_max ? 1 : 0;
+  sp->sample_ld = pl.nq_pad;
+  return TT_OK;
+}
+
+// Sample pass + selection.  thr != NULL: the query's threshold; topr != NULL (tile mode only): its
+// SHARD_TOPR largest sampled tile maxima, descending (sharded catalogs exchange these lists).
+int launch_sample(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr, float* topr,
+                  float* sample_buf, cudaStream_t st) {
   CUtensorMap tq, tx;
-  if (int e = make_tmap_bf16(&tq, qh, pl.nq_pad, pl.Dp, pl.block_m)) return e;
-  if (int e = make_tmap_bf16(&tx, Xh, N, pl.Dp, pl.pair ? BLOCK_N / 2 : BLOCK_N)) return e;
-
-  ScanParams sp{};
-  sp.N = N; sp.nq = nq; sp.num_kb = pl.num_kb; sp.num_stages = pl.num_stages; sp.nqu = pl.nqu;
-  sp.thr = thr; sp.seg_cnt = seg_cnt; sp.cand = reinterpret_cast<uint2*>(cand); sp.seg_cap = pl.seg_cap;
-  sp.sample_out = sample_buf;
-
-  if (pl.use_threshold) {
-    sp.num_slots = pl.sample_slots; sp.tile_stride = pl.sample_stride; sp.nslices = pl.sample_slices;
-    sp.sample_tile_max = pl.sample_tile_max ? 1 : 0;
-    sp.sample_ld = pl.nq_pad;
-    if (int e = launch_scan_mode<true>(pl, tq, tx, sp, pl.sample_slices * pl.nqu, st)) return e;
-    if (pl.sample_tile_max) {
-      const size_t sm = (size_t)pl.sample_slots * SEL_WQ * sizeof(float);
-      TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      select_threshold_tile_kernel<<<(nq + SEL_WQ - 1) / SEL_WQ, SEL_WQ * 32, sm, st>>>(sample_buf, pl.sample_slots, pl.nq_pad,
-                                                                                       nq, pl.sample_rank, thr);
-    } else {
-      const int nvals = pl.sample_slots * CHUNKS;
-      int npad = 1;
-      while (npad < nvals) npad <<= 1;
-      const size_t sm = (size_t)npad * sizeof(float);
-      TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      select_threshold_kernel<<<nq, 256, sm, st>>>(sample_buf, nvals, npad, pl.sample_rank, thr);
-    }
-    TT_CHECK_LAUNCH();
+  ScanParams sp;
+  if (int e = make_scan_params(pl, qh, Xh, N, nq, thr, nullptr, nullptr, sample_buf, &tq, &tx, &sp)) return e;
+  sp.num_slots = pl.sample_slots; sp.tile_stride = pl.sample_stride; sp.nslices = pl.sample_slices;
+  if (int e = launch_scan_mode<true>(pl, tq, tx, sp, pl.sample_slices * pl.nqu, st)) return e;
+  if (pl.sample_tile_max) {
+    const size_t sm = (size_t)pl.sample_slots * SEL_WQ * sizeof(float);
+    TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    select_threshold_tile_kernel<<<(nq + SEL_WQ - 1) / SEL_WQ, SEL_WQ * 32, sm, st>>>(
+        sample_buf, pl.sample_slots, pl.nq_pad, nq, topr ? min(pl.sample_rank, SHARD_TOPR) : pl.sample_rank, thr, topr,
+        SHARD_TOPR);
   } else {
-    fill_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thr, nq, -INFINITY);
-    TT_CHECK_LAUNCH();
+    TT_CHECK_ARG(topr == nullptr, "top-r lists need the tile sampling mode");
+    const int nvals = pl.sample_slots * CHUNKS;
+    int npad = 1;
+    while (npad < nvals) npad <<= 1;
+    const size_t sm = (size_t)npad * sizeof(float);
+    TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    select_threshold_kernel<<<nq, 256, sm, st>>>(sample_buf, nvals, npad, pl.sample_rank, thr);
   }
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}
+
+int launch_select_gathered(const float* topr_g, int G, int nq, int r, float* thr, cudaStream_t st) {
+  const size_t sm = (size_t)SEL_WQ * G * SHARD_TOPR * sizeof(float);
+  TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_gathered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  select_threshold_gathered_kernel<<<(nq + SEL_WQ - 1) / SEL_WQ, SEL_WQ * 32, sm, st>>>(topr_g, G, nq, r, thr);
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}
+
+int launch_main_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr,
+                     unsigned int* seg_cnt, void* cand, cudaStream_t st) {
+  CUtensorMap tq, tx;
+  ScanParams sp;
+  if (int e = make_scan_params(pl, qh, Xh, N, nq, thr, seg_cnt, cand, nullptr, &tq, &tx, &sp)) return e;
   sp.num_slots = pl.num_tiles; sp.tile_stride = 1; sp.nslices = pl.main_slices;
   profile_scan_begin(st);
   const int e = launch_scan_mode<false>(pl, tq, tx, sp, pl.main_slices * pl.nqu, st);
   profile_scan_end(st);
   return e;
+}
+
+int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq,
+                float* thr, unsigned int* seg_cnt, void* cand, float* sample_buf, cudaStream_t st) {
+  if (pl.use_threshold) {
+    if (int e = launch_sample(pl, qh, Xh, N, nq, thr, nullptr, sample_buf, st)) return e;
+  } else {
+    fill_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thr, nq, -INFINITY);
+    TT_CHECK_LAUNCH();
+  }
+  return launch_main_scan(pl, qh, Xh, N, nq, thr, seg_cnt, cand, st);
+}
+
+// Plan of one shard of a catalog of N_total rows: tiling and slicing follow the shard, the sampling
+// decisions (stride, rank, candidate target) follow the WHOLE catalog so that every rank samples the
+// same fraction of its rows and the gathered sample is the sample a single device would have drawn.
+ScanPlan make_shard_plan(long long N_local, long long N_total, int D, int nq, int K, bool* global_ok) {
+  ScanPlan pl = make_scan_plan(N_local, D, nq, K);
+  const ScanPlan gp = make_scan_plan(N_total, D, nq, K);
+  *global_ok = pl.supported && gp.use_threshold && !gp.route_exact && gp.sample_tile_max &&
+               gp.sample_rank <= SHARD_TOPR && N_local >= K;
+  if (!*global_ok) return pl;
+  pl.use_threshold = true;
+  pl.route_exact = false;
+  pl.target = gp.target;
+  pl.sample_stride = gp.sample_stride;
+  pl.sample_slots = (pl.num_tiles + gp.sample_stride - 1) / gp.sample_stride;
+  pl.sample_rank = gp.sample_rank;
+  pl.sample_tile_max = true;
+  pl.cand_cap = gp.cand_cap;
+  const int cap_units = pl.pair ? num_sms() / 2 : num_sms();
+  pl.sample_slices = pick_slices(pl.nqu, cap_units, pl.sample_slots);
+  // a shard may hold every candidate of a query (clustered catalogs): size its segments for the whole target
+  const long long slice_rows = ((long long)(pl.num_tiles + pl.main_slices - 1) / pl.main_slices) * BLOCK_N;
+  long long seg = 4LL * pl.target / pl.main_slices;
+  if (seg < 512) seg = 512;
+  if (seg > pl.cand_cap) seg = pl.cand_cap;
+  if (seg > slice_rows) seg = slice_rows;
+  pl.seg_cap = (int)((seg + 63) / 64 * 64);
+  return pl;
 }
 
 }  // namespace tt

@@ -105,28 +105,82 @@ class ShardedFlatIPIndex:
         else:
             dist.all_gather_into_tensor(gathered.view(-1), rec, group=self.group)
 
-    def search_device(self, q: torch.Tensor, k: int):
-        """q replicated on every rank -> global (scores, ids) [nq,k] on every rank, and the number of
-        queries that failed the global certificate and were re-run through the exact path."""
+    def _local_search(self, q: torch.Tensor, k: int, k_local: int, world: int, views) -> None:
+        """Fills this rank's record.  With every shard holding >= k rows and a plan for it, all ranks use ONE
+        threshold estimated from a sample of the whole catalog (a small all-gather of per-rank top-r sampled
+        scores): candidates per rank drop to ~1/G of the single-device count.  Otherwise each shard picks its
+        own threshold."""
+        scores, ids, bound, flags = views
+        nq = q.shape[0]
+        n_local_min = self.n_total - (world - 1) * (-(-self.n_total // world))     # the last shard is the smallest
+        plan_ok = getattr(self.local, "shard_plan_ok", None)
+        if world > 1 and k_local == k and plan_ok is not None and plan_ok(self.n_total, nq, k, max(n_local_min, 0)):
+            from ._native import TT_SHARD_TOPR
+            key = ("topr", nq, world)
+            bufs = self._bufs.get(key)
+            if bufs is None:
+                bufs = self._bufs[key] = (torch.empty((nq, TT_SHARD_TOPR), device=q.device, dtype=torch.float32),
+                                          torch.empty((world, nq, TT_SHARD_TOPR), device=q.device, dtype=torch.float32))
+            topr, topr_g = bufs
+            self.local.shard_sample(q, k, self.n_total, topr)
+            dist.all_gather_into_tensor(topr_g.view(-1), topr.view(-1), group=self.group)
+            self.local.shard_search_into(nq, k, self.n_total, topr_g, scores, ids, bound, flags)
+        else:
+            self.local.search_shard_into(q, k_local, scores, ids, bound, flags)
+
+    def search_async(self, q: torch.Tensor, k: int):
+        """Enqueues the whole sharded search (local search, all-gather, merge) and returns a PendingSearch;
+        `.result()` looks at the global certificate later (no host sync between consecutive batches)."""
+        from .vector_db import PendingSearch
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         nq = q.shape[0]
         lay, rec, gathered = self._buffers(nq, k, q.device, world)
-        scores, ids, bound, flags = record_views(rec, lay, nq, k)
+        views = record_views(rec, lay, nq, k)
+        scores, ids, bound, flags = views
         k_local = min(k, self.local.ntotal)
         if k_local < k:   # shard smaller than k: pad so every rank contributes [nq,k]
             scores.fill_(float("-inf"))
             ids.fill_(-1)
-        self.local.search_shard_into(q, k_local, scores, ids, bound, flags)
+        self._local_search(q, k, k_local, world, views)
         self._exchange(rec, gathered, world)
         s, i, fl, n_unc = self._merge(gathered, lay, nq, k)
-        n_bad = int(n_unc)                       # identical on every rank: all ranks merged the same records
-        if n_bad:
-            qsel = torch.nonzero(fl != 1).flatten().to(torch.int32)
-            self.local.search_exact_into(q, k_local, scores, ids, qsel)
-            bound[qsel.long()] = float("-inf")
-            flags[qsel.long()] = 1
-            self._exchange(rec, gathered, world)
-            s, i, fl, n_unc2 = self._merge(gathered, lay, nq, k)
+        post = getattr(self.local, "post_flag", None)
+        token = post(n_unc) if post is not None else None
+
+        def finish():
+            # identical on every rank: all ranks merged the same records
+            n_bad = self.local.read_flag(token) if token is not None else int(n_unc)
+            if not n_bad:
+                return s, i, 0
+            # Re-run the flagged queries alone (this rank's record buffer may already hold a later batch):
+            # exact fp32 search of every shard, a small exchange, merge, scatter into the result.
+            rows = torch.nonzero(fl != 1).flatten()
+            nsel = int(rows.numel())
+            lay2 = record_layout(nsel, k)
+            rec2 = torch.zeros(lay2.nbytes, dtype=torch.uint8, device=q.device)
+            gathered2 = torch.zeros((world, lay2.nbytes), dtype=torch.uint8, device=q.device)
+            s_l, i_l, b_l, f_l = record_views(rec2, lay2, nsel, k)
+            s_l.fill_(float("-inf"))
+            i_l.fill_(-1)
+            b_l.fill_(float("-inf"))
+            f_l.fill_(1)
+            self.local.search_exact_into(q[rows].contiguous(), k_local, s_l, i_l,
+                                         torch.arange(nsel, device=q.device, dtype=torch.int32))
+            self._exchange(rec2, gathered2, world)
+            s2, i2, fl2, n_unc2 = self._merge(gathered2, lay2, nsel, k)
             if int(n_unc2):
                 raise RuntimeError("sharded search: queries still uncertified after the exact re-run")
-        return s, i, n_bad
+            s[rows] = s2
+            i[rows] = i2
+            return s, i, n_bad
+        return PendingSearch(finish)
+
+    def search_device(self, q: torch.Tensor, k: int):
+        """q replicated on every rank -> global (scores, ids) [nq,k] on every rank, and the number of
+        queries that failed the global certificate and were re-run through the exact path."""
+        return self.search_async(q, k).result()
+
+    def search_host_async(self, q, k: int):
+        """numpy in / numpy out round trip (pinned staging), asynchronous; `.result()` -> (scores, ids, n_rerun)."""
+        from .vector_db import host_search_async
+        return host_search_async(self, self.search_async, self.local.device, self.local.d, q, k)

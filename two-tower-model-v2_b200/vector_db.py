@@ -55,6 +55,43 @@ def read_flat_ip_file(path: str) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------------------------
+class _FlagRing:
+    """A few pinned int32 slots: the certificate count of a search is copied into one of them
+    asynchronously, so the host can look at it later without draining the stream."""
+
+    def __init__(self, n: int = 16):
+        self.host = torch.zeros(n, dtype=torch.int32, pin_memory=True)
+        self.n, self.next = n, 0
+
+    def post(self, nunc_dev: torch.Tensor):
+        slot = self.next
+        self.next = (self.next + 1) % self.n
+        self.host[slot:slot + 1].copy_(nunc_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return slot, ev
+
+    def read(self, slot: int, ev) -> int:
+        ev.synchronize()
+        return int(self.host[slot])
+
+
+class PendingSearch:
+    """Result of an asynchronous search.  `result()` waits for THIS search only (not for work enqueued
+    after it), re-runs uncertified queries through the exact path and returns (scores, ids, n_rerun)."""
+
+    def __init__(self, finish):
+        self._finish = finish
+        self._out = None
+
+    def result(self):
+        if self._out is None:
+            self._out = self._finish()
+            self._finish = None
+        return self._out
+
+
+# ---------------------------------------------------------------------------------------------
 class FlatIPIndex:
     """Device-resident exact inner-product index (stands where faiss.IndexFlatIP stood).
 
@@ -74,7 +111,7 @@ class FlatIPIndex:
         self.id_offset = 0
         self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
         self._exact_ws: Optional[torch.Tensor] = None
-        self._pinned: Dict[Tuple[str, int, int], torch.Tensor] = {}
+        self._ring: Optional[_FlagRing] = None
 
     # -- size ------------------------------------------------------------------------------
     @property
@@ -247,44 +284,116 @@ class FlatIPIndex:
                                                   ops._stream()), "tt_flat_scan_scores")
         return out
 
+    def search_async(self, q: torch.Tensor, k: int) -> PendingSearch:
+        """Enqueues a search and returns at once; `.result()` checks the certificate later, so a caller can
+        keep the next batch's kernels queued behind this one (no idle GPU between batches)."""
+        scores, ids, flags, nunc = self.search_device(q, k)
+        if self._ring is None:
+            self._ring = _FlagRing()
+        slot, ev = self._ring.post(nunc)
+
+        def finish():
+            n_bad = self._ring.read(slot, ev)
+            if n_bad:
+                qsel = torch.nonzero(flags != 1).flatten().to(torch.int32)
+                self.search_exact_device(q, k, scores, ids, qsel)
+            return scores, ids, n_bad
+        return PendingSearch(finish)
+
     def search_checked_device(self, q: torch.Tensor, k: int):
         """search_device + re-run of uncertified queries through the exact path (one host sync)."""
-        scores, ids, flags, nunc = self.search_device(q, k)
-        n_bad = int(nunc.item())
-        if n_bad:
-            qsel = torch.nonzero(flags != 1).flatten().to(torch.int32)
-            self.search_exact_device(q, k, scores, ids, qsel)
-        return scores, ids, n_bad
+        return self.search_async(q, k).result()
 
-    def _pin(self, tag: str, shape: Tuple[int, int], dtype) -> torch.Tensor:
-        key = (tag, shape[0], shape[1])
-        t = self._pinned.get(key)
-        if t is None:
-            t = torch.empty(shape, dtype=dtype, pin_memory=True)
-            if len(self._pinned) > 24:
-                self._pinned.clear()
-            self._pinned[key] = t
-        return t
+    def post_flag(self, nunc_dev: torch.Tensor):
+        if self._ring is None:
+            self._ring = _FlagRing()
+        return self._ring.post(nunc_dev)
+
+    def read_flag(self, token) -> int:
+        return self._ring.read(*token)
+
+    # -- sharded catalogs: one threshold for the whole catalog (tt_flat_shard_*) ---------------------
+    def shard_plan_ok(self, n_total: int, nq: int, k: int, n_local_min: int) -> bool:
+        return bool(_native.load().tt_flat_shard_plan_ok(int(n_local_min), int(n_total), self.d, int(nq), int(k)))
+
+    def _shard_workspace(self, n_total: int, nq: int, k: int) -> torch.Tensor:
+        key = ("shard", n_total, nq, k)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = int(_native.load().tt_flat_shard_workspace_bytes(self.ntotal, n_total, self.d, nq, k))
+            ws = torch.empty(max(nbytes, 256), device=self.device, dtype=torch.uint8)
+            if len(self._ws) > 8:
+                self._ws.clear()
+            self._ws[key] = ws
+        return ws
+
+    def shard_sample(self, q: torch.Tensor, k: int, n_total: int, topr: torch.Tensor) -> None:
+        """Phase 1 of the sharded search: fills topr f32 [nq, TT_SHARD_TOPR] (this shard's largest sampled scores)."""
+        q = ops._f32c(q, "queries")
+        ws = self._shard_workspace(n_total, q.shape[0], k)
+        with torch.cuda.device(self.device):
+            _native.check(_native.load().tt_flat_shard_sample(
+                q.data_ptr(), q.shape[0], self.xh.data_ptr(), self.stats.data_ptr(), self.ntotal, n_total, self.d, k,
+                topr.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream()), "tt_flat_shard_sample")
+
+    def shard_search_into(self, nq: int, k: int, n_total: int, topr_g: torch.Tensor, scores: torch.Tensor,
+                          ids: torch.Tensor, bound: torch.Tensor, flags: torch.Tensor) -> None:
+        """Phase 2: global threshold from the gathered lists [G, nq, TT_SHARD_TOPR], main scan, finalize into
+        the record views (scores/ids must be contiguous [nq,k])."""
+        ws = self._shard_workspace(n_total, nq, k)
+        nunc = torch.empty((1,), device=self.device, dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            _native.check(_native.load().tt_flat_shard_search(
+                nq, self.xn.data_ptr(), self.xh.data_ptr(), self.ntotal, n_total, self.d, k, self.id_offset,
+                topr_g.data_ptr(), topr_g.shape[0], scores.data_ptr(), ids.data_ptr(), flags.data_ptr(), nunc.data_ptr(),
+                bound.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream()), "tt_flat_shard_search")
+
+    def search_host_async(self, q: np.ndarray, k: int) -> PendingSearch:
+        """Host-to-host search, asynchronous: stages q through pinned memory, enqueues H2D + search + D2H and
+        returns; `.result()` -> (scores, ids, n_rerun) numpy arrays.  Up to 3 calls may be in flight."""
+        return host_search_async(self, self.search_async, self.device, self.d, q, k)
 
     def search(self, q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
         """Host-to-host search, the shape of faiss `index.search(q, k)`: q f32 [nq,d] (un-normalised:
         the device op applies q/(||q||+1e-8)) -> (scores f32 [nq,k], ids i64 [nq,k])."""
-        q = np.ascontiguousarray(q, dtype=np.float32)
-        if q.ndim != 2 or q.shape[1] != self.d:
-            raise ValueError(f"expected queries [nq, {self.d}], got {q.shape}")
-        nq = q.shape[0]
-        if nq == 0:
-            return np.empty((0, k), np.float32), np.empty((0, k), np.int64)
-        hq = self._pin("q", (nq, self.d), torch.float32)
-        hq.copy_(torch.from_numpy(q))
-        dq = hq.to(self.device, non_blocking=True)
-        scores, ids, _ = self.search_checked_device(dq, k)
-        hs = self._pin("s", (nq, k), torch.float32)
-        hi = self._pin("i", (nq, k), torch.int64)
+        scores, ids, _ = self.search_host_async(q, k).result()
+        return scores, ids
+
+
+def host_search_async(owner, search_async, device, d: int, q: np.ndarray, k: int, depth: int = 3) -> PendingSearch:
+    """Shared host round trip of FlatIPIndex / ShardedFlatIPIndex: pinned staging buffers in a ring of `depth`
+    sets per (nq, k) so that consecutive batches overlap their copies with the previous batch's kernels."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    if q.ndim != 2 or q.shape[1] != d:
+        raise ValueError(f"expected queries [nq, {d}], got {q.shape}")
+    nq = q.shape[0]
+    if nq == 0:
+        empty = (np.empty((0, k), np.float32), np.empty((0, k), np.int64), 0)
+        return PendingSearch(lambda: empty)
+    rings = owner.__dict__.setdefault("_host_rings", {})
+    ring = rings.get((nq, k))
+    if ring is None:
+        if len(rings) > 8:
+            rings.clear()
+        ring = rings[(nq, k)] = {"next": 0, "sets": [
+            (torch.empty((nq, d), dtype=torch.float32, pin_memory=True),
+             torch.empty((nq, k), dtype=torch.float32, pin_memory=True),
+             torch.empty((nq, k), dtype=torch.int64, pin_memory=True)) for _ in range(depth)]}
+    hq, hs, hi = ring["sets"][ring["next"]]
+    ring["next"] = (ring["next"] + 1) % depth
+    hq.copy_(torch.from_numpy(q))
+    dq = hq.to(device, non_blocking=True)
+    pending = search_async(dq, k)
+
+    def finish():
+        scores, ids, n_bad = pending.result()        # exact re-run (if any) is enqueued before the copies below
         hs.copy_(scores, non_blocking=True)
         hi.copy_(ids, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return hs.numpy().copy(), hi.numpy().copy()
+        ev = torch.cuda.Event()
+        ev.record()
+        ev.synchronize()
+        return hs.numpy().copy(), hi.numpy().copy(), n_bad
+    return PendingSearch(finish)
 
 
 # ---------------------------------------------------------------------------------------------
