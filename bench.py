@@ -369,7 +369,8 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 scan + f32 rescoring",
             "data": "synthetic",
             "config": {"workload": f"flat_ip_top{k}_{n_total}x{d}_nq{nq}", "catalog_rows": n_total, "dim": d, "topk": k,
-                       "query_batch": nq, "sharding": f"catalog rows over {world} GPU(s), all-gather + merge" if world > 1 else "none",
+                       "query_batch": nq, "sharding": (f"catalog rows over {world} GPUs, one catalog-wide threshold, all-gather ({sharded.exchange_used}) + certified merge"
+                                    if world > 1 else "none"),
                        "l2": "inputs (7.68 GB bf16 per pass) exceed L2; no flush"},
             "e2e": e2e, "gpu_launches": int(launches), "uncertified_queries": uncertified,
             "roofline": roofline, "clocks": clk.summary()}

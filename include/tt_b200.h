@@ -192,6 +192,28 @@ int tt_shard_merge(const void* gathered, size_t rank_stride, size_t off_scores, 
                    size_t off_bound, size_t off_flags, int G, int nq, int K,
                    float* scores, int64_t* ids, int32_t* flags, int32_t* n_uncertified, void* stream);
 
+/* All-gather of per-rank records over NVLink peer memory by our own kernels (the exchange of the sharded
+ * search; NCCL stays available as the alternative).  The caller owns, on every rank, a receive buffer and
+ * an int32 flag array [G] that are mapped into every peer (CUDA IPC) and double-buffered by sequence parity.
+ *   tt_p2p_push  copies `src` (nbytes, multiple of 16) into peer_dst[g] for every g (host arrays of G device
+ *                pointers: my slot in rank g's receive buffer / my flag cell in rank g's flag array), then
+ *                publishes `seq` in the flags with system-scope release stores.  done_counter: u32 device
+ *                scalar, zero-initialised, private to this stream.
+ *   tt_p2p_wait  one-warp kernel: returns when flags[g] >= seq for every g (acquire loads); after
+ *                timeout_seconds it gives up and writes seq to *timed_out (device i32, 0 = fine) instead of
+ *                hanging the device.  Kernels enqueued after it may read the receive buffer. */
+int tt_p2p_enable_peer(int peer_device);   /* cudaDeviceEnablePeerAccess from the current device (idempotent) */
+/* Receive-buffer plumbing: tt_p2p_alloc = cudaMalloc (zero-filled) + its 64-byte CUDA IPC handle; tt_p2p_open maps
+ * another rank's handle into the CURRENT device's address space with peer access; close / free undo them. */
+int tt_p2p_alloc(size_t bytes, void** dev_ptr, void* handle64);
+int tt_p2p_open(const void* handle64, void** dev_ptr);
+int tt_p2p_close(void* dev_ptr);
+int tt_p2p_free(void* dev_ptr);
+int tt_p2p_push(const void* src, size_t nbytes, void* const* peer_dst, int32_t* const* peer_flag, int G,
+                int32_t seq, uint32_t* done_counter, void* stream);
+int tt_p2p_wait(const int32_t* flags, int G, int32_t seq, double timeout_seconds, int32_t* timed_out,
+                void* stream);
+
 /* Measurement hooks (bench.py).  tt_kernel_launch_count: kernels this library has launched in this
  * process.  tt_profile_scan_arm(n): the next n main-scan launches of tt_flat_search are bracketed by
  * CUDA events on their stream; tt_profile_scan_read: waits for them, writes their durations in ms,

@@ -43,7 +43,8 @@ def main():
         exact_ok = bool((ei == i[:16]).all()) and bool((es - s[:16]).abs().max() <= 1e-6)
         ok = same_ids and same_scores and exact_ok
         print(f"world={world} N={n_total} D={d} nq={nq} K={k}: sharded==single ids {same_ids} scores {same_scores}; "
-              f"vs fp32 exact path (16 queries) {exact_ok}; uncertified local {n_bad} single {fbad}", flush=True)
+              f"vs fp32 exact path (16 queries) {exact_ok}; uncertified local {n_bad} single {fbad}; exchange {sharded.exchange_used}"
+              + (f" (p2p unavailable: {sharded._p2p_error})" if hasattr(sharded, "_p2p_error") else ""), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)

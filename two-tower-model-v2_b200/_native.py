@@ -40,6 +40,13 @@ SIGNATURES = {
                                      c_void_p, c_size_t, c_void_p]),
     "tt_flat_shard_search": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_void_p, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tt_p2p_enable_peer": (c_int, [c_int]),
+    "tt_p2p_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
+    "tt_p2p_open": (c_int, [c_void_p, c_void_p]),
+    "tt_p2p_close": (c_int, [c_void_p]),
+    "tt_p2p_free": (c_int, [c_void_p]),
+    "tt_p2p_push": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_int32, c_void_p, c_void_p]),
+    "tt_p2p_wait": (c_int, [c_void_p, c_int, c_int32, ctypes.c_double, c_void_p, c_void_p]),
     "tt_shard_merge": (c_int, [c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tt_flat_search_exact_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),

@@ -359,19 +359,28 @@ shard_merge_kernel(const unsigned char* __restrict__ gathered, size_t rank_strid
   extern __shared__ __align__(16) unsigned char msm[];
   unsigned long long* key = reinterpret_cast<unsigned long long*>(msm);   // [G][K]
   __shared__ int s_valid[64];
+  __shared__ int s_flag[64];
+  __shared__ float s_bound[64];
   __shared__ float s_fk;
   const int q = blockIdx.x;
   const int n = G * K;
   if (threadIdx.x == 0) s_fk = -INFINITY;
-  if (threadIdx.x < 64) s_valid[threadIdx.x] = 0;
+  if (threadIdx.x < G) {
+    const unsigned char* rec = gathered + (size_t)threadIdx.x * rank_stride;
+    s_flag[threadIdx.x] = reinterpret_cast<const int*>(rec + off_flags)[q];
+    s_bound[threadIdx.x] = reinterpret_cast<const float*>(rec + off_bound)[q];
+    s_valid[threadIdx.x] = 0;
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int g = i / K, j = i % K;
     const unsigned char* rec = gathered + (size_t)g * rank_stride;
-    const long long id = reinterpret_cast<const long long*>(rec + off_ids)[(long long)q * K + j];
+    const long long* idp = reinterpret_cast<const long long*>(rec + off_ids) + (long long)q * K;
+    const long long id = idp[j];
     const float sc = reinterpret_cast<const float*>(rec + off_scores)[(long long)q * K + j];
     key[i] = (id >= 0) ? make_key(sc, (uint32_t)id) : 0ull;
-    if (id >= 0) atomicAdd(&s_valid[g], 1);
+    // lists are padded at the tail: the last valid position marks the list's length (no atomics)
+    if (id >= 0 && (j == K - 1 || idp[j + 1] < 0)) s_valid[g] = j + 1;
   }
   __syncthreads();
   int total = 0;
@@ -381,10 +390,11 @@ shard_merge_kernel(const unsigned char* __restrict__ gathered, size_t rank_strid
     if (ki == 0ull) continue;
     const int g = i / K;
     int rank = i % K;
-    for (int h = 0; h < G; ++h) {
+    // binary search every other list for the number of larger keys; stop once the element is out of the top K
+    for (int h = 0; h < G && rank < K; ++h) {
       if (h == g) continue;
       const unsigned long long* lst = key + h * K;
-      int lo = 0, hi = s_valid[h];          // number of keys of list h that are larger than ki
+      int lo = 0, hi = s_valid[h];
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (lst[mid] > ki) lo = mid + 1; else hi = mid; }
       rank += lo;
     }
@@ -403,10 +413,9 @@ shard_merge_kernel(const unsigned char* __restrict__ gathered, size_t rank_strid
     int why = 0;
     float bmax = -INFINITY;
     for (int g = 0; g < G; ++g) {
-      const unsigned char* rec = gathered + (size_t)g * rank_stride;
-      const int f = reinterpret_cast<const int*>(rec + off_flags)[q];
+      const int f = s_flag[g];
       if (f <= 0) why |= (-f) & (1 | 4);     // local "fewer than K" / local f_K checks are superseded by the global one
-      bmax = fmaxf(bmax, reinterpret_cast<const float*>(rec + off_bound)[q]);
+      bmax = fmaxf(bmax, s_bound[g]);
     }
     if (total < K) why |= 2;
     if (total >= K && !(bmax == -INFINITY) && !(s_fk >= bmax)) why |= 8;

@@ -99,7 +99,8 @@ def topk_merge(scores_g: torch.Tensor, ids_g: torch.Tensor) -> Tuple[torch.Tenso
     return scores, ids
 
 
-def shard_merge(gathered: torch.Tensor, off_scores: int, off_ids: int, off_bound: int, off_flags: int, nq: int, K: int):
+def shard_merge(gathered: torch.Tensor, off_scores: int, off_ids: int, off_bound: int, off_flags: int, nq: int, K: int,
+                nunc: torch.Tensor = None):
     """[G, record bytes] all-gathered shard records -> (scores [nq,K], ids [nq,K], flags [nq], n_uncertified [1])
     with the global exactness certificate (tt_shard_merge)."""
     G, stride = gathered.shape
@@ -107,7 +108,9 @@ def shard_merge(gathered: torch.Tensor, off_scores: int, off_ids: int, off_bound
     scores = torch.empty((nq, K), device=dev, dtype=torch.float32)
     ids = torch.empty((nq, K), device=dev, dtype=torch.int64)
     flags = torch.empty((max(nq, 1),), device=dev, dtype=torch.int32)
-    nunc = torch.empty((1,), device=dev, dtype=torch.int32)
+    if nunc is None:
+        nunc = torch.empty((1,), device=dev, dtype=torch.int32)
+    stride = gathered.stride(0)
     with torch.cuda.device(dev):
         _native.check(_native.load().tt_shard_merge(gathered.data_ptr(), stride, off_scores, off_ids, off_bound, off_flags,
                                                     G, nq, K, scores.data_ptr(), ids.data_ptr(), flags.data_ptr(),

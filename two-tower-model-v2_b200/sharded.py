@@ -18,6 +18,8 @@ from __future__ import annotations
 
 from typing import Callable, NamedTuple, Optional, Tuple
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -62,9 +64,106 @@ def record_views(buf: torch.Tensor, lay: RecordLayout, nq: int, k: int):
             field(lay.off_bound, nq, torch.float32, (nq,)), field(lay.off_flags, nq, torch.int32, (nq,)))
 
 
-def _merge_cuda(gathered: torch.Tensor, lay: RecordLayout, nq: int, k: int):
+def _merge_cuda(gathered: torch.Tensor, lay: RecordLayout, nq: int, k: int, nunc: Optional[torch.Tensor] = None):
     from . import ops
-    return ops.shard_merge(gathered, lay.off_scores, lay.off_ids, lay.off_bound, lay.off_flags, nq, k)
+    return ops.shard_merge(gathered, lay.off_scores, lay.off_ids, lay.off_bound, lay.off_flags, nq, k, nunc)
+
+
+class _RawCudaBuffer:
+    """__cuda_array_interface__ over a raw device pointer (uint8), for a zero-copy torch view."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class P2PExchange:
+    """All-gather of fixed-size records over NVLink peer memory with our own kernels (tt_p2p_push /
+    tt_p2p_wait) instead of NCCL.
+
+    Every rank owns one device buffer holding, per channel, a double-buffered receive area [2][G][nbytes] and
+    flags int32 [2][G].  The buffers are mapped into every rank through CUDA IPC handles exchanged once over
+    the process group (tt_p2p_alloc / tt_p2p_open); afterwards an exchange is two kernel launches
+    on the caller's stream and no host synchronisation: push my record into my slot on every peer and raise
+    my sequence flag there; wait (one warp, acquire loads, bounded by a time-out) until every rank's flag for
+    this sequence number is up.  `status[1]` turns non-zero if a wait timed out.
+    """
+
+    def __init__(self, channel_bytes, device: torch.device, group=None, timeout_s: float = 20.0):
+        from . import _native
+        self.lib = _native.load()
+        self.check = _native.check
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = device
+        self.timeout_s = timeout_s
+        G = self.world
+        self.nbytes = [int(b) for b in channel_bytes]
+        assert all(b % 16 == 0 for b in self.nbytes)
+        self.recv_off, self.flag_off = [], []
+        off = 0
+        for b in self.nbytes:
+            self.recv_off.append(off)
+            off += 2 * G * b
+            off = (off + 255) // 256 * 256
+        for _ in self.nbytes:
+            self.flag_off.append(off)
+            off += 2 * G * 4
+            off = (off + 255) // 256 * 256
+        import ctypes
+        self._ctypes = ctypes
+        self.total_bytes = off
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            self.check(self.lib.tt_p2p_alloc(off, ctypes.byref(ptr), handle), "tt_p2p_alloc")
+        self.base = int(ptr.value)
+        handles = [None] * G
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.peer_base = []
+        for r in range(G):
+            if r == self.rank:
+                self.peer_base.append(self.base)
+                continue
+            p = ctypes.c_void_p()
+            with torch.cuda.device(device):
+                self.check(self.lib.tt_p2p_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(p)), "tt_p2p_open")
+            self.peer_base.append(int(p.value))
+        # zero-copy torch view of the local buffer (kernels downstream take torch tensors)
+        self.buf = torch.as_tensor(_RawCudaBuffer(self.base, off), device=device)
+        self.done = torch.zeros(len(self.nbytes), dtype=torch.int32, device=device)
+        self.seq = [0] * len(self.nbytes)
+        self._ptr_arrays = {}
+        dist.barrier(group=group)       # every rank has mapped every buffer before the first push
+
+    def _ptrs(self, ch: int, parity: int):
+        key = (ch, parity)
+        arr = self._ptr_arrays.get(key)
+        if arr is None:
+            G, b = self.world, self.nbytes[ch]
+            c = self._ctypes
+            dst = (c.c_void_p * G)(*[p + self.recv_off[ch] + (parity * G + self.rank) * b for p in self.peer_base])
+            flg = (c.c_void_p * G)(*[p + self.flag_off[ch] + (parity * G + self.rank) * 4 for p in self.peer_base])
+            arr = self._ptr_arrays[key] = (dst, flg)
+        return arr
+
+    def all_gather(self, ch: int, src: torch.Tensor, status: torch.Tensor) -> torch.Tensor:
+        """src: this rank's record (uint8 [nbytes[ch]], 16-byte aligned) -> uint8 [G, nbytes[ch]] view of this
+        rank's receive buffer, valid for kernels enqueued after this call on the current stream."""
+        G, b = self.world, self.nbytes[ch]
+        assert src.numel() * src.element_size() == b
+        self.seq[ch] += 1
+        seq = self.seq[ch]
+        parity = seq & 1
+        dst, flg = self._ptrs(ch, parity)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            self.check(self.lib.tt_p2p_push(src.data_ptr(), b, dst, flg, G, seq, self.done[ch:ch + 1].data_ptr(), stream),
+                       "tt_p2p_push")
+            my_flags = self.base + self.flag_off[ch] + parity * G * 4
+            self.check(self.lib.tt_p2p_wait(my_flags, G, seq, self.timeout_s, status[1:2].data_ptr(), stream), "tt_p2p_wait")
+        o = self.recv_off[ch] + parity * G * b
+        return self.buf[o:o + G * b].view(G, b)
 
 
 class ShardedFlatIPIndex:
@@ -76,12 +175,17 @@ class ShardedFlatIPIndex:
     `merge(gathered[G,nbytes] uint8, layout, nq, k) -> (scores, ids, flags, n_uncertified)`.
     """
 
-    def __init__(self, local_index, n_total: int, group=None, merge: Optional[Callable] = None):
+    def __init__(self, local_index, n_total: int, group=None, merge: Optional[Callable] = None, exchange: str = "auto"):
         self.local = local_index
         self.n_total = int(n_total)
         self.group = group
         self._merge = merge if merge is not None else _merge_cuda
         self._bufs = {}
+        self._p2p = {}
+        # "p2p": our push/wait kernels over NVLink peer memory; "nccl": torch.distributed all-gather.
+        # "auto" tries p2p on CUDA and falls back to nccl if the IPC set-up fails.
+        self.exchange = os.environ.get("TT_B200_EXCHANGE", exchange)
+        self.exchange_used = None
 
     @property
     def ntotal(self) -> int:
@@ -105,7 +209,30 @@ class ShardedFlatIPIndex:
         else:
             dist.all_gather_into_tensor(gathered.view(-1), rec, group=self.group)
 
-    def _local_search(self, q: torch.Tensor, k: int, k_local: int, world: int, views) -> None:
+    def _p2p_for(self, nq: int, k: int, device, world: int, lay: RecordLayout):
+        """The P2PExchange for this (nq, k) shape (channel 0: top-r lists, channel 1: result records), or None
+        when the NCCL path is to be used.  Created collectively: every rank reaches this with the same shape."""
+        if world == 1 or device.type != "cuda" or self.exchange == "nccl" or self._merge is not _merge_cuda:
+            self.exchange_used = self.exchange_used or "nccl"
+            return None
+        key = (nq, k, world)
+        if key not in self._p2p:
+            from ._native import TT_SHARD_TOPR
+            ok, ex = 1, None
+            try:
+                ex = P2PExchange([nq * TT_SHARD_TOPR * 4, lay.nbytes], device, self.group)
+            except Exception as e:     # IPC not permitted, no peer access, ...
+                if self.exchange == "p2p":
+                    raise
+                self._p2p_error = repr(e)
+                ok = 0
+            flag = torch.tensor([ok], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)     # all ranks take the same path
+            self._p2p[key] = ex if int(flag.item()) == 1 else None
+            self.exchange_used = "p2p" if self._p2p[key] is not None else "nccl"
+        return self._p2p[key]
+
+    def _local_search(self, q: torch.Tensor, k: int, k_local: int, world: int, views, p2p=None, status=None) -> None:
         """Fills this rank's record.  With every shard holding >= k rows and a plan for it, all ranks use ONE
         threshold estimated from a sample of the whole catalog (a small all-gather of per-rank top-r sampled
         scores): candidates per rank drop to ~1/G of the single-device count.  Otherwise each shard picks its
@@ -123,7 +250,10 @@ class ShardedFlatIPIndex:
                                           torch.empty((world, nq, TT_SHARD_TOPR), device=q.device, dtype=torch.float32))
             topr, topr_g = bufs
             self.local.shard_sample(q, k, self.n_total, topr)
-            dist.all_gather_into_tensor(topr_g.view(-1), topr.view(-1), group=self.group)
+            if p2p is not None:
+                topr_g = p2p.all_gather(0, topr.view(torch.uint8).view(-1), status).view(torch.float32).view(world, nq, TT_SHARD_TOPR)
+            else:
+                dist.all_gather_into_tensor(topr_g.view(-1), topr.view(-1), group=self.group)
             self.local.shard_search_into(nq, k, self.n_total, topr_g, scores, ids, bound, flags)
         else:
             self.local.search_shard_into(q, k_local, scores, ids, bound, flags)
@@ -141,15 +271,28 @@ class ShardedFlatIPIndex:
         if k_local < k:   # shard smaller than k: pad so every rank contributes [nq,k]
             scores.fill_(float("-inf"))
             ids.fill_(-1)
-        self._local_search(q, k, k_local, world, views)
-        self._exchange(rec, gathered, world)
-        s, i, fl, n_unc = self._merge(gathered, lay, nq, k)
+        p2p = self._p2p_for(nq, k, q.device, world, lay)
+        if p2p is not None:
+            status = self._bufs.setdefault(("status", nq, k, world), torch.zeros(2, dtype=torch.int32, device=q.device))
+            self._local_search(q, k, k_local, world, views, p2p, status)
+            gathered = p2p.all_gather(1, rec, status)
+            s, i, fl, n_unc = self._merge(gathered, lay, nq, k, status[0:1])
+            n_unc = status
+        else:
+            self._local_search(q, k, k_local, world, views)
+            self._exchange(rec, gathered, world)
+            s, i, fl, n_unc = self._merge(gathered, lay, nq, k)
         post = getattr(self.local, "post_flag", None)
         token = post(n_unc) if post is not None else None
 
         def finish():
             # identical on every rank: all ranks merged the same records
-            n_bad = self.local.read_flag(token) if token is not None else int(n_unc)
+            st = self.local.read_flag(token) if token is not None else int(n_unc)
+            if isinstance(st, list):
+                if st[1]:
+                    raise RuntimeError(f"sharded search: peer exchange {st[1]} timed out (a rank is missing)")
+                st = st[0]
+            n_bad = st
             if not n_bad:
                 return s, i, 0
             # Re-run the flagged queries alone (this rank's record buffer may already hold a later batch):

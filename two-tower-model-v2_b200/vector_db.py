@@ -56,24 +56,27 @@ def read_flat_ip_file(path: str) -> np.ndarray:
 
 # ---------------------------------------------------------------------------------------------
 class _FlagRing:
-    """A few pinned int32 slots: the certificate count of a search is copied into one of them
-    asynchronously, so the host can look at it later without draining the stream."""
+    """A few pinned int32 slots: the status words of a search (uncertified count[, exchange time-out]) are
+    copied into one of them asynchronously, so the host can look at them later without draining the stream."""
+    WIDTH = 2
 
     def __init__(self, n: int = 16):
-        self.host = torch.zeros(n, dtype=torch.int32, pin_memory=True)
+        self.host = torch.zeros((n, self.WIDTH), dtype=torch.int32, pin_memory=True)
         self.n, self.next = n, 0
 
-    def post(self, nunc_dev: torch.Tensor):
+    def post(self, status_dev: torch.Tensor):
         slot = self.next
         self.next = (self.next + 1) % self.n
-        self.host[slot:slot + 1].copy_(nunc_dev, non_blocking=True)
+        w = int(status_dev.numel())
+        self.host[slot, :w].copy_(status_dev, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        return slot, ev
+        return slot, ev, w
 
-    def read(self, slot: int, ev) -> int:
+    def read(self, slot: int, ev, w: int = 1):
         ev.synchronize()
-        return int(self.host[slot])
+        vals = self.host[slot, :w].tolist()
+        return vals[0] if w == 1 else vals
 
 
 class PendingSearch:
@@ -290,10 +293,10 @@ class FlatIPIndex:
         scores, ids, flags, nunc = self.search_device(q, k)
         if self._ring is None:
             self._ring = _FlagRing()
-        slot, ev = self._ring.post(nunc)
+        token = self._ring.post(nunc)
 
         def finish():
-            n_bad = self._ring.read(slot, ev)
+            n_bad = self._ring.read(*token)
             if n_bad:
                 qsel = torch.nonzero(flags != 1).flatten().to(torch.int32)
                 self.search_exact_device(q, k, scores, ids, qsel)
