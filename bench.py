@@ -38,7 +38,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -49,7 +49,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
         except Exception:
@@ -190,6 +190,52 @@ def batch_sweep(index, lib, peaks, n_total, d, k, nqs, steps=10):
                     "scan_hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"], "scan_bf16_tflops": tfl,
                     "tensor_frac_sustained": tfl / peaks["bf16_tflops_sustained"],
                     "uncertified": int(torch.stack(nunc).sum().item())})
+    return out
+
+
+def bench_retrieve_path(index, d, k, requests=200, batch=1024):
+    """Secondary (BASELINE config C5 shape on one GPU): the /retrieve path = history rows -> fused gather+pool ->
+    exact top-K, host to host.  Batch-1 latency percentiles and batch-1024 throughput, 50-event histories."""
+    import two_tower_model_v2_b200 as pkg
+    db = pkg.VectorDatabase(d)
+    db.index, db.product_ids, db.id_to_index, db.index_to_id = index, [], {}, {}
+    out = {}
+    for method in ("weighted_avg", "attention"):
+        torch.manual_seed(0)
+        tower = pkg.BuyerTower(d, method).cuda()
+        pipe = pkg.RetrievalPipeline(tower, db)
+        S, n = 50, index.ntotal
+        g = torch.Generator().manual_seed(99)
+        w_choices = torch.tensor([1.0, 5.0, 10.0])
+
+        def make(B):
+            idx = torch.randint(0, n, (B, S), generator=g, dtype=torch.int64).pin_memory()
+            w = w_choices[torch.multinomial(torch.tensor([0.75, 0.18, 0.07]), B * S, True, generator=g)].view(B, S).pin_memory()
+            return idx, w
+
+        def request(idx, w):
+            s, i, _ = pipe.retrieve_device_async(idx.cuda(non_blocking=True), w.cuda(non_blocking=True), k).result()
+            return s.cpu(), i.cpu()
+        reqs = [make(1) for _ in range(requests + 10)]
+        for r in reqs[:10]:
+            request(*r)
+        lat = []
+        for r in reqs[10:]:
+            t = time.perf_counter()
+            request(*r)
+            lat.append((time.perf_counter() - t) * 1e3)
+        lat = np.sort(np.array(lat))
+        big = [make(batch) for _ in range(8)]
+        request(*big[0]); request(*big[1])
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for r in big[2:]:
+            request(*r)
+        thr = batch * 6 / (time.perf_counter() - t)
+        out[method] = {"batch1_latency_ms": {"p50": float(lat[len(lat) // 2]), "p99": float(lat[int(len(lat) * 0.99) - 1]),
+                                             "mean": float(lat.mean())},
+                       f"batch{batch}_requests_per_s": thr}
+    out["config"] = f"history 50 events, top-{k}, {index.ntotal}x{d} catalog, host round trip per request, 1 GPU"
     return out
 
 
@@ -377,6 +423,7 @@ def main():
     if world == 1 and not args.no_secondary:
         line["secondary"] = {"pooling": bench_pooling(peaks),
                              "query_batch_sweep": batch_sweep(index, lib, peaks, n_total, d, k, [1, 128, 1024])}
+        line["secondary"]["retrieve_path"] = bench_retrieve_path(index, d, k)
         line["cpu_baseline"] = cpu_baseline_search(n_total, d, nq, k)
     print(json.dumps(line), flush=True)
     if world > 1:

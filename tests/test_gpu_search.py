@@ -299,3 +299,39 @@ def test_shard_global_threshold_path(N, D, nq, k, G):
     # every shard used the same threshold: the bounds differ only through the local prune cutoff
     _, _, bg, _ = record_views(gathered, lay, nq, k)
     assert torch.isfinite(bg).all()
+
+
+@pytest.mark.parametrize("method", ["weighted_avg", "attention"])
+def test_retrieval_pipeline_matches_encode_then_search_oracle(method):
+    """history ids -> fused gather+pool -> search on the device == oracle pooling of the catalog rows + oracle search."""
+    import two_tower_model_v2_b200 as pkg
+    from oracle import buyer_tower_oracle as bo
+    rng = np.random.default_rng(21)
+    N, D, B, S, k = 30000, 384, 16, 50, 10
+    cat = rng.standard_normal((N, D)).astype(np.float32)
+    ids = [f"p{i}" for i in range(N)]
+    db = pkg.VectorDatabase(D)
+    db.build_index(cat, ids)
+    torch.manual_seed(3)
+    tower = pkg.BuyerTower(D, method).to(dev())
+    pipe = pkg.RetrievalPipeline(tower, db)
+    events = ["view", "add_to_cart", "purchase"]
+    rows = rng.integers(0, N, (B, S))
+    ev = rng.integers(0, 3, (B, S))
+    lens = rng.integers(1, S + 1, B)
+    batch = [[{"product_id": ids[rows[b, s]], "event_type": events[ev[b, s]]} for s in range(lens[b])] for b in range(B)]
+    got = pipe.retrieve_batch(batch, k)
+    xn = fo.normalize_rows(cat)
+    wts = np.array([1.0, 5.0, 10.0], np.float32)
+    for b in range(B):
+        x = xn[rows[b, :lens[b]]][None]
+        w = wts[ev[b, :lens[b]]][None]
+        if method == "weighted_avg":
+            emb = bo.weighted_average(x, w)
+        else:
+            emb = bo.attention_aggregation(x, w, *[p.detach().cpu().numpy() for p in tower.attention.parameters()])
+        rs, ri = fo.search(xn, fo.normalize_rows(emb), k)
+        assert [p for p, _ in got[b]] == [ids[i] for i in ri[0]], f"buyer {b}"
+        assert np.allclose([s for _, s in got[b]], rs[0], atol=1e-5)
+    one = pipe.retrieve(batch[0], k)
+    assert [p for p, _ in one] == [p for p, _ in got[0]]

@@ -126,3 +126,27 @@ def test_search_planner_invariants():
     # units fill the machine: one unit per SM (single) / SM pair (pair) on a 148-SM part
     assert _plan(10_000_000, 384, 128, 100)["main_slices"] == 148
     assert _plan(10_000_000, 384, 256, 100)["main_slices"] == 74
+
+
+def test_retrieval_pipeline_history_encoding():
+    """encode_histories mirrors encoder.py:263-273: timestamp sort only when every interaction has one, last
+    `max_interaction_history` kept, event weights by name, unknown ids -> row -1 / counted, padding (-1, 0)."""
+    from two_tower_model_v2_b200.retrieval import RetrievalPipeline
+
+    class _Db:
+        id_to_index = {"a": 0, "b": 1, "c": 2}
+    pipe = RetrievalPipeline.__new__(RetrievalPipeline)
+    pipe.db, pipe.max_history = _Db(), 3
+    pipe.config = {"event_weights": {"view": 1, "add_to_cart": 5, "purchase": 10}}
+    batch = [
+        [{"product_id": "c", "event_type": "purchase", "timestamp": "2024-01-03"},
+         {"product_id": "a", "event_type": "view", "timestamp": "2024-01-01"},
+         {"product_id": "b", "event_type": "AddToCart", "timestamp": "2024-01-02"},
+         {"product_id": "zz", "event_type": "buy", "timestamp": "2024-01-04"}],
+        [{"product_id": "b", "event_type": "wishlist"}, {"product_id": "a", "event_type": "view", "timestamp": "2020"}],
+        [],
+    ]
+    idx, w, unknown = pipe.encode_histories(batch)
+    assert idx.tolist() == [[1, 2, -1], [1, 0, -1], [-1, -1, -1]]       # sorted, truncated to the last 3; unsorted; empty
+    assert w.tolist() == [[5.0, 10.0, 10.0], [1.0, 1.0, 0.0], [0.0, 0.0, 0.0]]
+    assert unknown == 1 and idx.dtype.name == "int64" and w.dtype.name == "float32"

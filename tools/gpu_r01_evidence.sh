@@ -18,4 +18,6 @@ done
 C="$B --nq 4096"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"flat_finalize_kernel|select_threshold_kernel" -s 6 -c 2 -f -o $O/finalize_nq4096 $C > $O/ncu_finalize.log 2>&1
 timeout 600 python tools/sweep.py 1000000 384 > $O/sweep_1M.log 2>&1
+timeout 600 python tools/sweep.py 10000000 384 > $O/sweep_10M.log 2>&1
+timeout 600 python tools/sweep.py 10000000 768 1,64,128,1024,1024,4096 > $O/sweep_10M_768.log 2>&1
 tail -n 3 $O/t_gpu.log $O/smoke.log; tail -c 1500 $O/bench_default.log; tail -n 2 $O/bench_reference.log; ls -la $O

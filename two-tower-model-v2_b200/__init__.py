@@ -12,8 +12,9 @@ The directory is named `two-tower-model-v2_b200`; import it as `two_tower_model_
 """
 from .buyer_tower import BuyerTower
 from .config import get_event_weight
+from .retrieval import RetrievalPipeline
 from .sharded import ShardedFlatIPIndex, shard_bounds
 from .vector_db import FlatIPIndex, VectorDatabase, read_flat_ip_file, write_flat_ip_file
 
-__all__ = ["BuyerTower", "VectorDatabase", "FlatIPIndex", "ShardedFlatIPIndex", "shard_bounds",
+__all__ = ["BuyerTower", "VectorDatabase", "FlatIPIndex", "ShardedFlatIPIndex", "RetrievalPipeline", "shard_bounds",
            "get_event_weight", "read_flat_ip_file", "write_flat_ip_file"]
