@@ -40,7 +40,7 @@ def test_pool_matches_reference_golden(case, method):
     if method == "attention":
         seq = m.encode_from_sequence(x[0], w[0])           # [S,D],[S] -> [1,D]
         assert tuple(seq.shape) == (1, g["x"].shape[2])
-        assert rel_err(seq.cpu().numpy(), g["attention_seq0"]) < TOL
+        assert rel_err(seq.detach().cpu().numpy(), g["attention_seq0"]) < TOL
 
 
 def test_zero_weights_give_exact_zero():
@@ -63,7 +63,7 @@ def test_pool_matches_oracle_seeded(B, S, D, H):
     torch.manual_seed(B + S)
     m = pkg.BuyerTower(D, "attention", H).to(dev())
     params = [p.detach().cpu().numpy() for p in m.attention.parameters()]
-    out = m(xt, wt).cpu().numpy()
+    out = m(xt, wt).detach().cpu().numpy()
     ref = bo.attention_aggregation(x.astype(np.float64), w.astype(np.float64), *[p.astype(np.float64) for p in params])
     assert rel_err(out, ref) < TOL
 
@@ -88,7 +88,7 @@ def test_gather_variant_matches_dense(method):
     params = [p.detach().cpu().numpy() for p in m.parameters()] if method == "attention" else None
     ref = bo.forward(x, w, method, params)
     assert np.abs(out - ref).max() < TOL
-    dense = m(torch.from_numpy(x).to(dev()), torch.from_numpy(w).to(dev())).cpu().numpy()
+    dense = m(torch.from_numpy(x).to(dev()), torch.from_numpy(w).to(dev())).detach().cpu().numpy()
     assert np.abs(out - dense).max() < 2e-6
 
 
@@ -112,4 +112,33 @@ def test_c2_full_size_properties(method):
     sel = torch.arange(0, B, 97, device=dev())
     params = [p.detach().cpu().numpy() for p in m.parameters()] if method == "attention" else None
     ref = bo.forward(x[sel].cpu().numpy(), w[sel].cpu().numpy(), method, params)
-    assert rel_err(out[sel].cpu().numpy(), ref) < TOL
+    assert rel_err(out[sel].detach().cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("method", ["weighted_avg", "attention"])
+def test_backward_matches_reference_formulation(method):
+    """Training callers (two_tower.py:212): forward through the fused kernels, gradients equal to autograd of
+    the reference arithmetic (x, and the attention MLP parameters)."""
+    import two_tower_model_v2_b200 as pkg
+    from two_tower_model_v2_b200.buyer_tower import _eager_pool
+    torch.manual_seed(5)
+    dev = torch.device("cuda:0")
+    B, S, D = 6, 17, 384
+    x = torch.randn(B, S, D, device=dev, requires_grad=True)
+    w = torch.tensor([1.0, 5.0, 10.0], device=dev)[torch.randint(0, 3, (B, S), device=dev)]
+    tower = pkg.BuyerTower(D, method).to(dev)
+    out = tower(x, w)
+    t = torch.randn_like(out)
+    (out * t).sum().backward()
+    gx = x.grad.clone()
+    gp = [p.grad.clone() for p in tower.parameters()]
+    x2 = x.detach().clone().requires_grad_(True)
+    params = [p.detach().clone().requires_grad_(True) for p in tower.parameters()]
+    ref = _eager_pool(x2, w, tuple(params) if params else None)
+    (ref * t).sum().backward()
+    assert torch.allclose(out, ref, atol=1e-6)
+    assert torch.allclose(gx, x2.grad, atol=1e-6, rtol=1e-4)
+    for a, b in zip(gp, params):
+        assert torch.allclose(a, b.grad, atol=1e-6, rtol=1e-4)
+    with torch.no_grad():                                   # inference path unchanged: no graph, same numbers
+        assert torch.equal(tower(x, w), out.detach())

@@ -100,3 +100,18 @@ def test_ties_are_ordered_by_id_and_tolerated():
     s2, i2 = fo.search(x2, q, 3)
     ok, _ = fo.compare_topk(np.array([[1, 1, 0.5]], np.float32), np.array([[0, 1, 5]]), s2, i2, x2, q)
     assert not ok                      # a non-tied intruder is rejected
+
+
+@pytest.mark.parametrize("name", ["buyer_tower_b8_s50_d384.npz", "buyer_tower_ragged.npz", "buyer_tower_zero_weight_row.npz"])
+def test_eager_backward_formulation_matches_reference_outputs(name):
+    """The differentiable restatement used by the backward pass (buyer_tower._eager_pool) reproduces the real
+    reference module's outputs (golden vectors), so its autograd gradients are the reference's gradients."""
+    import torch
+    from two_tower_model_v2_b200.buyer_tower import _eager_pool
+    g = golden(name)
+    x, w = torch.from_numpy(g["x"]), torch.from_numpy(g["w"])
+    wa = _eager_pool(x, w).numpy()
+    assert rel_err(wa, g["weighted_avg"]) < 1e-5
+    mlp = tuple(torch.from_numpy(g[k]) for k in ("W1", "b1", "W2", "b2"))
+    at = _eager_pool(x, w, mlp).numpy()
+    assert rel_err(at, g["attention"]) < 1e-5

@@ -45,6 +45,14 @@ def main():
         print(f"world={world} N={n_total} D={d} nq={nq} K={k}: sharded==single ids {same_ids} scores {same_scores}; "
               f"vs fp32 exact path (16 queries) {exact_ok}; uncertified local {n_bad} single {fbad}; exchange {sharded.exchange_used}"
               + (f" (p2p unavailable: {sharded._p2p_error})" if hasattr(sharded, "_p2p_error") else ""), flush=True)
+    if nq % world == 0:          # sliced host API: every rank submits its share and gets its share back
+        nl = nq // world
+        hs, hi, _ = sharded.search_host_sliced_async(q.cpu().numpy()[rank * nl:(rank + 1) * nl], k).result()
+        same = bool((torch.from_numpy(hi).cuda() == i[rank * nl:(rank + 1) * nl]).all()) and \
+            bool((torch.from_numpy(hs).cuda() == s[rank * nl:(rank + 1) * nl]).all())
+        ok = ok and same
+        if rank == 0:
+            print(f"sliced host API == replicated device API on rank 0's share: {same}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)

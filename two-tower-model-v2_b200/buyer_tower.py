@@ -6,6 +6,9 @@ method names, argument meaning and exceptions.  The arithmetic runs in hand-writ
 kernels (csrc/pool.cu, csrc/attn_logits.cu) through the C-ABI; there is no CPU path: CPU tensors
 raise RuntimeError.
 
+Training callers work too: under autograd the forward still runs the fused kernels and the backward
+recomputes the reference formulation in eager torch (`_FusedPool`).
+
 Beyond the reference surface: `precompute_item_logits` / `forward_gather` pool
 straight out of a device-resident item-embedding table given history row indices, so a request
 never re-encodes history items (reference: src/inference/encoder.py:276-303).
@@ -18,6 +21,46 @@ import torch
 import torch.nn as nn
 
 from . import ops
+
+
+def _eager_pool(x: torch.Tensor, w: torch.Tensor, mlp=None) -> torch.Tensor:
+    """The reference arithmetic in differentiable torch ops (buyer_tower.py:58-66 / :85-99).  Used ONLY inside
+    the backward pass (recompute + autograd); the forward always runs the fused CUDA kernels."""
+    if mlp is None:
+        nw = w.unsqueeze(-1) / (w.unsqueeze(-1).sum(dim=1, keepdim=True) + 1e-8)
+        y = (x * nw).sum(dim=1)
+    else:
+        W1, b1, W2, b2 = mlp
+        logits = torch.relu(x @ W1.t() + b1) @ W2.reshape(-1, 1) + b2
+        a = torch.softmax(logits.squeeze(-1) * w, dim=1)
+        y = (x * a.unsqueeze(-1)).sum(dim=1)
+    return torch.nn.functional.normalize(y, p=2, dim=1)
+
+
+class _FusedPool(torch.autograd.Function):
+    """Forward: fused sm_100a kernels (no [B,S,D] temporary, no graph).  Backward (training callers of the
+    reference: src/models/two_tower.py:212, src/training/trainer.py:216-236): recompute the reference
+    formulation in eager torch and differentiate it - exact gradients, the cost of one eager forward+backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, *mlp):
+        ctx.save_for_backward(x, w, *mlp)
+        if mlp:
+            B, S, D = x.shape
+            logits = ops.attention_logits(x.view(B * S, D), mlp[0], mlp[1], mlp[2].reshape(-1), mlp[3]).view(B, S)
+            return ops.pool_attention(x, logits, w)
+        return ops.pool_weighted(x, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, *mlp = ctx.saved_tensors
+        needs = ctx.needs_input_grad
+        with torch.enable_grad():
+            ins = [t.detach().requires_grad_(needs[i]) for i, t in enumerate((x, w, *mlp))]
+            out = _eager_pool(ins[0], ins[1], tuple(ins[2:]) if mlp else None)
+            wanted = [t for t in ins if t.requires_grad]
+            grads = iter(torch.autograd.grad(out, wanted, g.contiguous()))
+        return tuple(next(grads) if t.requires_grad else None for t in ins)
 
 
 class BuyerTower(nn.Module):
@@ -62,12 +105,19 @@ class BuyerTower(nn.Module):
     def weighted_average(self, item_embeddings: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
         """buyer_tower.py:43-68."""
         x, w = self._prep(item_embeddings, weights)
+        if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+            return _FusedPool.apply(x, w).to(item_embeddings.dtype)
         return ops.pool_weighted(x, w).to(item_embeddings.dtype)
 
     def attention_aggregation(self, item_embeddings: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
         """buyer_tower.py:70-101."""
         x, w = self._prep(item_embeddings, weights)
         B, S, D = x.shape
+        l1, l2 = self.attention[0], self.attention[2]
+        if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or l1.weight.requires_grad):
+            # training: keep the parameters in the graph (the reference trains this MLP, trainer.py:216-236)
+            return _FusedPool.apply(x, w, l1.weight.float(), l1.bias.float(), l2.weight.float(), l2.bias.float()) \
+                .to(item_embeddings.dtype)
         W1, b1, W2, b2 = self._mlp_params(x.device)
         logits = ops.attention_logits(x.view(B * S, D), W1, b1, W2, b2).view(B, S)
         return ops.pool_attention(x, logits, w).to(item_embeddings.dtype)

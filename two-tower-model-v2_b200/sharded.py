@@ -327,3 +327,48 @@ class ShardedFlatIPIndex:
         """numpy in / numpy out round trip (pinned staging), asynchronous; `.result()` -> (scores, ids, n_rerun)."""
         from .vector_db import host_search_async
         return host_search_async(self, self.search_async, self.local.device, self.local.d, q, k)
+
+    def search_host_sliced_async(self, q_local, k: int):
+        """Serving layout for G ranks fronting one sharded catalog: every rank submits ITS share of the batch
+        (numpy [nq_local, D], the same row count on every rank).  The shares are all-gathered on the device (rank
+        order = batch order), the whole batch is searched as usual, and each rank gets back the results of its own
+        rows: host copies are nq_local*D*4 bytes in and nq_local*k*12 bytes out per rank instead of the whole batch
+        on every rank.  `.result()` -> (scores [nq_local,k], ids [nq_local,k], n_rerun) numpy."""
+        import numpy as np
+        from .vector_db import PendingSearch
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        dev, d = self.local.device, self.local.d
+        q_local = np.ascontiguousarray(q_local, dtype=np.float32)
+        if q_local.ndim != 2 or q_local.shape[1] != d:
+            raise ValueError(f"expected queries [nq_local, {d}], got {q_local.shape}")
+        nl = q_local.shape[0]
+        rings = self.__dict__.setdefault("_sliced_rings", {})
+        ring = rings.get((nl, k))
+        if ring is None:
+            if len(rings) > 8:
+                rings.clear()
+            ring = rings[(nl, k)] = {"next": 0, "sets": [
+                (torch.empty((nl, d), dtype=torch.float32, pin_memory=True),
+                 torch.empty((nl, k), dtype=torch.float32, pin_memory=True),
+                 torch.empty((nl, k), dtype=torch.int64, pin_memory=True)) for _ in range(3)]}
+        hq, hs, hi = ring["sets"][ring["next"]]
+        ring["next"] = (ring["next"] + 1) % 3
+        hq.copy_(torch.from_numpy(q_local))
+        dq_local = hq.to(dev, non_blocking=True)
+        dq_all = torch.empty((world, nl, d), device=dev, dtype=torch.float32)    # fresh: the exact re-run may need it later
+        if world > 1:
+            dist.all_gather_into_tensor(dq_all.view(-1), dq_local.view(-1), group=self.group)
+        else:
+            dq_all[0].copy_(dq_local)
+        pending = self.search_async(dq_all.view(world * nl, d), k)
+
+        def finish():
+            scores, ids, n_bad = pending.result()
+            hs.copy_(scores[rank * nl:(rank + 1) * nl], non_blocking=True)
+            hi.copy_(ids[rank * nl:(rank + 1) * nl], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            ev.synchronize()
+            return hs.numpy().copy(), hi.numpy().copy(), n_bad
+        return PendingSearch(finish)
