@@ -42,7 +42,8 @@ def check(idx, x, q, k, expect_certified=True):
 # ---- the scan kernel itself: raw bf16 tensor-core scores vs the same arithmetic in torch ----------
 @pytest.mark.parametrize("N,D,nq", [(256, 64, 128), (1000, 64, 5), (2048, 384, 128), (5000, 384, 1),
                                       (3000, 384, 200), (1500, 100, 70), (4096, 768, 64), (2000, 768, 100),
-                                      (777, 512, 33), (1000, 1024, 64)])
+                                      (777, 512, 33), (1000, 1024, 64),
+                                      (3000, 768, 300), (2500, 640, 129), (1800, 1024, 257), (1500, 704, 200)])
 def test_scan_scores_match_bf16_reference(N, D, nq):
     rng = np.random.default_rng(N + D + nq)
     x = rng.standard_normal((N, D)).astype(np.float32)
@@ -66,6 +67,7 @@ def test_scan_scores_match_bf16_reference(N, D, nq):
     (20000, 384, 2000, 10),    # C1 full query count (16 query blocks)
     (100000, 384, 1, 100), (100000, 384, 7, 100), (100000, 384, 129, 100), (50000, 384, 300, 1),
     (30000, 768, 50, 100),     # C4 width (M=64 path)
+    (60000, 768, 300, 100),    # C4 width, CTA pairs with a half-resident query block
     (30000, 100, 33, 37),      # D not a multiple of 64
     (9000, 64, 16, 1000),      # API maximum k (server.py:46)
     (70000, 256, 40, 500),

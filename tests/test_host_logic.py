@@ -108,8 +108,9 @@ def test_search_planner_invariants():
                         (10_000_000, 384, 129, 100), (10_000_000, 768, 300, 100)]:
         p = _plan(N, D, nq, K)
         assert p["supported"] == 1 and p["smem"] <= 227 * 1024 and p["stages"] >= 2
-        # CTA pairs (256 queries per unit) exactly when nq > 128 and the 128-query operand fits (D <= 512)
-        want = 64 if D > 512 else (256 if nq > 128 else 128)
+        # CTA pairs (256 queries per unit) exactly when nq > 128 (rows wider than 640 stream part of the query
+        # block); single CTAs keep 128 resident queries while >= 3 full stages fit (D <= 512), else 64
+        want = 256 if nq > 128 else (64 if D > 512 else 128)
         assert p["unit_queries"] == want
         assert p["k_blocks"] == -(-D // 64) and p["tiles"] == -(-N // 256)
         assert p["query_units"] == -(-nq // want)

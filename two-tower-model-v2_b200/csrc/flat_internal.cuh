@@ -14,6 +14,7 @@ constexpr int FINALIZE_MAX_CAND = 16384;   // candidates per query the finalize 
 // Everything the host decides about one search call (pure function of N, D, nq, K and the SM count).
 struct ScanPlan {
   int Dp, num_kb, block_m, num_stages;
+  int num_kb_res, stage_bytes;   // resident query K-blocks; ring stride (see ScanParams)
   bool supported;
   bool pair;           // 2-CTA clusters running cta_group::2 MMAs (nq > 128)
   size_t smem_bytes;

@@ -59,7 +59,10 @@ struct ScanParams {
   long long N;            // catalog rows
   int nq;                 // valid queries
   int num_kb;             // K-blocks per row (Dp / 64)
-  int num_stages;         // B ring depth
+  int num_kb_res;         // leading K-blocks of the query block that stay resident in shared memory; the
+                          // rest (D > 640 in pair mode) is streamed with the catalog, once per tile, from L2
+  int stage_bytes;        // ring stride: the catalog K-block, plus room for a query K-block when streaming
+  int num_stages;         // ring depth
   int nqu;                // query units (query blocks, or query-block pairs)
   int nslices;            // catalog slices
   int num_slots;          // tiles to visit in total (main: all tiles; sample: sampled tiles)
@@ -139,8 +142,8 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   // 128B-swizzled operand tiles need 1024-byte alignment (identical offsets in both CTAs of a pair)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + (size_t)p.num_kb * A_KB_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.num_stages * B_STAGE_BYTES);
+  uint8_t* smem_b = smem_a + (size_t)p.num_kb_res * A_KB_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.num_stages * p.stage_bytes);
   uint64_t* full_bar = bars;                       // [MAX_STAGES]
   uint64_t* empty_bar = bars + MAX_STAGES;         // [MAX_STAGES]
   uint64_t* a_full_bar = bars + 2 * MAX_STAGES;    // [1]
@@ -193,8 +196,8 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (lane == 0) {
       // In pair mode every TMA of either CTA signals the LEADER's barrier (the MMA issuer waits there).
       const uint32_t a_bar = smem_u32(a_full_bar);
-      if (leader) mbar_arrive_expect_tx(a_bar, (uint32_t)(p.num_kb * A_KB_BYTES) * (PAIR ? 2u : 1u));
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      if (leader) mbar_arrive_expect_tx(a_bar, (uint32_t)(p.num_kb_res * A_KB_BYTES) * (PAIR ? 2u : 1u));
+      for (int kb = 0; kb < p.num_kb_res; ++kb) {
         if (PAIR) tma_load_2d_2cta(smem_u32(smem_a + (size_t)kb * A_KB_BYTES), &tmap_q, a_bar, kb * BLOCK_K, qb * BLOCK_M);
         else      tma_load_2d(smem_u32(smem_a + (size_t)kb * A_KB_BYTES), &tmap_q, a_bar, kb * BLOCK_K, qb * BLOCK_M);
       }
@@ -207,9 +210,15 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1, 100 + stage);
           const uint32_t fb = smem_u32(full_bar + stage);
-          if (leader) mbar_arrive_expect_tx(fb, (uint32_t)B_STAGE_BYTES * (PAIR ? 2u : 1u));
-          if (PAIR) tma_load_2d_2cta(smem_u32(smem_b + (size_t)stage * B_STAGE_BYTES), &tmap_x, fb, kb * BLOCK_K, row0);
-          else      tma_load_2d(smem_u32(smem_b + (size_t)stage * B_STAGE_BYTES), &tmap_x, fb, kb * BLOCK_K, row0);
+          const bool stream_a = kb >= p.num_kb_res;
+          const uint32_t dst = smem_u32(smem_b + (size_t)stage * p.stage_bytes);
+          if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(B_STAGE_BYTES + (stream_a ? A_KB_BYTES : 0)) * (PAIR ? 2u : 1u));
+          if (PAIR) tma_load_2d_2cta(dst, &tmap_x, fb, kb * BLOCK_K, row0);
+          else      tma_load_2d(dst, &tmap_x, fb, kb * BLOCK_K, row0);
+          if (stream_a) {   // this K-block of the query block rides along (L2-resident after the first tile)
+            if (PAIR) tma_load_2d_2cta(dst + B_STAGE_BYTES, &tmap_q, fb, kb * BLOCK_K, qb * BLOCK_M);
+            else      tma_load_2d(dst + B_STAGE_BYTES, &tmap_q, fb, kb * BLOCK_K, qb * BLOCK_M);
+          }
           if (PAIR && !leader) mbar_arrive_remote(fb, 0);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
@@ -236,8 +245,9 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           mbar_wait(smem_u32(full_bar + stage), phase, 220 + stage);
           tc_fence_after();
           // descriptor start-address field is in 16-byte units
-          const uint64_t a_desc = a_desc0 + (uint64_t)((kb * A_KB_BYTES) >> 4);
-          const uint64_t b_desc = b_desc0 + (uint64_t)((stage * B_STAGE_BYTES) >> 4);
+          const uint64_t b_desc = b_desc0 + (uint64_t)((stage * p.stage_bytes) >> 4);
+          const uint64_t a_desc = (kb < p.num_kb_res) ? a_desc0 + (uint64_t)((kb * A_KB_BYTES) >> 4)
+                                                      : b_desc + (uint64_t)(B_STAGE_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 bytes per K=16 step
@@ -614,17 +624,34 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   pl.Dp = (int)tt_flat_pitch(D);
   pl.num_kb = pl.Dp / BLOCK_K;
   const int sms = num_sms();
-  // A (queries) stays resident: M=128 per CTA while it leaves room for >= 3 full-tile B stages, else M=64.
   const int budget = 227 * 1024 - 1024 /*align*/ - BAR_BYTES - SCRATCH_BYTES;
+  const int kb_bytes_m128 = 128 * BLOCK_K * 2;                 // one K-block of a 128-query block: 16 KB
+  const int b_full = BLOCK_N * BLOCK_K * 2, b_half = b_full / 2;
   pl.block_m = 128;
-  if (budget - pl.num_kb * 128 * 128 < 3 * (BLOCK_N * BLOCK_K * 2)) pl.block_m = 64;
-  pl.pair = (pl.block_m == 128) && (nq > 128) && (sms >= 2);
-  const int b_stage = (pl.pair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
-  const int a_bytes = pl.num_kb * pl.block_m * 128;
-  pl.num_stages = (budget - a_bytes) / b_stage;
+  pl.num_kb_res = pl.num_kb;
+  pl.pair = (nq > 128) && (sms >= 2);
+  if (pl.pair) {
+    // 2-CTA tiling, 128 queries per CTA.  The query block stays resident while it leaves room for 4 half-tile
+    // stages (D <= 640); wider rows keep the leading K-blocks resident and stream the rest with the catalog.
+    if (pl.num_kb * kb_bytes_m128 + 4 * b_half <= budget) {
+      pl.stage_bytes = b_half;
+    } else {
+      pl.stage_bytes = b_half + kb_bytes_m128;
+      pl.num_kb_res = (budget - 4 * pl.stage_bytes) / kb_bytes_m128;
+      if (pl.num_kb_res < 0) pl.num_kb_res = 0;
+      if (pl.num_kb_res > pl.num_kb) pl.num_kb_res = pl.num_kb;
+    }
+  } else {
+    // single-CTA tiling (HBM-bound batches): resident query block of 128 rows while it leaves room for >= 3
+    // full-tile stages, else 64 rows.
+    if (budget - pl.num_kb * kb_bytes_m128 < 3 * b_full) pl.block_m = 64;
+    pl.stage_bytes = b_full;
+  }
+  const int a_bytes = pl.num_kb_res * pl.block_m * BLOCK_K * 2;
+  pl.num_stages = (budget - a_bytes) / pl.stage_bytes;
   if (pl.num_stages > MAX_STAGES) pl.num_stages = MAX_STAGES;
   pl.supported = pl.num_stages >= 2;
-  pl.smem_bytes = (size_t)a_bytes + (size_t)pl.num_stages * b_stage + 1024 /*align*/ + BAR_BYTES + SCRATCH_BYTES;
+  pl.smem_bytes = (size_t)a_bytes + (size_t)pl.num_stages * pl.stage_bytes + 1024 /*align*/ + BAR_BYTES + SCRATCH_BYTES;
   pl.nqb = (nq + pl.block_m - 1) / pl.block_m;
   if (pl.pair) pl.nqb = (pl.nqb + 1) / 2 * 2;
   pl.nq_pad = pl.nqb * pl.block_m;
@@ -753,6 +780,7 @@ static int make_scan_params(const ScanPlan& pl, const void* qh, const void* Xh, 
   if (int e = make_tmap_bf16(tx, Xh, N, pl.Dp, pl.pair ? BLOCK_N / 2 : BLOCK_N)) return e;
   *sp = ScanParams{};
   sp->N = N; sp->nq = nq; sp->num_kb = pl.num_kb; sp->num_stages = pl.num_stages; sp->nqu = pl.nqu;
+  sp->num_kb_res = pl.num_kb_res; sp->stage_bytes = pl.stage_bytes;
   sp->thr = thr; sp->seg_cnt = seg_cnt; sp->cand = reinterpret_cast<uint2*>(cand); sp->seg_cap = pl.seg_cap;
   sp->sample_out = sample_buf;
   sp->sample_tile_max = pl.sample_tile_max ? 1 : 0;
