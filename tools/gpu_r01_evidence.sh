@@ -17,6 +17,8 @@ for NQ in 4096 128 1; do
 done
 C="$B --nq 4096"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"flat_finalize_kernel|select_threshold_kernel" -s 6 -c 2 -f -o $O/finalize_nq4096 $C > $O/ncu_finalize.log 2>&1
+timeout 300 python tools/pool_only.py > $O/pool_plain.log 2>&1 &&
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"pool_vec_kernel|attn_logits" -s 8 -c 3 -f -o $O/pool_c2 python tools/pool_only.py > $O/ncu_pool.log 2>&1
 timeout 600 python tools/sweep.py 1000000 384 > $O/sweep_1M.log 2>&1
 timeout 600 python tools/sweep.py 10000000 384 > $O/sweep_10M.log 2>&1
 timeout 600 python tools/sweep.py 10000000 768 1,64,128,1024,1024,4096 > $O/sweep_10M_768.log 2>&1

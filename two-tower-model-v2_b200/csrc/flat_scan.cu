@@ -316,18 +316,26 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             while (hitmask) {
               const int src = __ffs(hitmask) - 1;
               hitmask &= hitmask - 1;
+              // which 32-column halves of the hit lane qualify (usually one): only those are spilled and re-read
+              const unsigned int halves = __shfl_sync(0xffffffffu, (m0 >= thr ? 1u : 0u) | (m1 >= thr ? 2u : 0u), src);
               if (lane == src) {
+                if (halves & 1u) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  *reinterpret_cast<uint4*>(scratch + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
-                  *reinterpret_cast<uint4*>(scratch + 32 + j) = make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
+                  for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(scratch + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+                }
+                if (halves & 2u) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(scratch + 32 + j) = make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
                 }
               }
               __syncwarp();
               const float thr_s = __shfl_sync(0xffffffffu, thr, src);
               const unsigned int cnt_s = __shfl_sync(0xffffffffu, my_cnt, src);
               const int q_s = __shfl_sync(0xffffffffu, q, src);
-              const uint32_t x0 = scratch[lane], x1 = scratch[32 + lane];
+              const uint32_t x0 = (halves & 1u) ? scratch[lane] : 0xff800000u;          // -inf: never qualifies
+              const uint32_t x1 = (halves & 2u) ? scratch[32 + lane] : 0xff800000u;
               const bool h0 = __uint_as_float(x0) >= thr_s, h1 = __uint_as_float(x1) >= thr_s;
               const unsigned int b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
               const unsigned int lt = (1u << lane) - 1u;
