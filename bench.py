@@ -237,6 +237,38 @@ def bench_retrieve_path(index, d, k, requests=200, batch=1024):
         out[method] = {"batch1_latency_ms": {"p50": float(lat[len(lat) // 2]), "p99": float(lat[int(len(lat) * 0.99) - 1]),
                                              "mean": float(lat.mean())},
                        f"batch{batch}_requests_per_s": thr}
+        if method == "weighted_avg":
+            # 64 single-request clients (threads) sharing catalog passes through the micro-batcher
+            import threading
+
+            def batch_fn(payloads, kk):
+                idx = torch.from_numpy(np.stack([p[0] for p in payloads])).pin_memory().cuda(non_blocking=True)
+                w = torch.from_numpy(np.stack([p[1] for p in payloads])).pin_memory().cuda(non_blocking=True)
+                s, i, _ = pipe.retrieve_device_async(idx, w, kk).result()
+                s, i = s.cpu().numpy(), i.cpu().numpy()
+                return [list(zip(i[r].tolist(), s[r].tolist())) for r in range(len(payloads))]
+            clients, per_client = 64, 30
+            payloads = [[(reqs[(c * per_client + j) % len(reqs)][0][0].numpy(), reqs[(c * per_client + j) % len(reqs)][1][0].numpy())
+                         for j in range(per_client)] for c in range(clients)]
+            lat_mb = []
+            with pkg.MicroBatcher(batch_fn, max_batch=128, max_wait_ms=0.3) as mb:
+                mb(payloads[0][0], k)
+
+                def client(c):
+                    for pl in payloads[c]:
+                        t0 = time.perf_counter()
+                        mb(pl, k)
+                        lat_mb.append((time.perf_counter() - t0) * 1e3)
+                ths = [threading.Thread(target=client, args=(c,)) for c in range(clients)]
+                t = time.perf_counter()
+                [th.start() for th in ths]
+                [th.join() for th in ths]
+                el = time.perf_counter() - t
+                lat_mb = np.sort(np.array(lat_mb))
+                out["micro_batched_64_clients"] = {"requests_per_s": clients * per_client / el,
+                                                   "mean_batch": (mb.requests - 1) / max(mb.batches - 1, 1),
+                                                   "latency_ms": {"p50": float(lat_mb[len(lat_mb) // 2]),
+                                                                  "p99": float(lat_mb[int(len(lat_mb) * 0.99) - 1])}}
     out["config"] = f"history 50 events, top-{k}, {index.ntotal}x{d} catalog, host round trip per request, 1 GPU"
     return out
 

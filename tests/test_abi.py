@@ -57,3 +57,18 @@ def test_sass_is_blackwell_native():
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnemonic in sass, f"{mnemonic} missing from SASS"
     assert "HMMA.16" not in sass, "legacy mma.sync path found"
+
+
+def test_torch_ops_are_cuda_only():
+    """Every op is registered under torch.ops.tt and has no CPU (or Meta) implementation: CPU tensors fail loudly."""
+    import pytest
+    import torch
+    import two_tower_model_v2_b200  # noqa: F401
+    for name in ("pool_weighted", "pool_weighted_gather", "attention_logits", "pool_attention", "pool_attention_gather",
+                 "topk_merge", "flat_build", "flat_search", "flat_search_exact"):
+        assert hasattr(torch.ops.tt, name), name
+    with pytest.raises(NotImplementedError):
+        torch.ops.tt.pool_weighted(torch.zeros(1, 2, 4), torch.ones(1, 2))
+    with pytest.raises(NotImplementedError):
+        torch.ops.tt.flat_search(torch.zeros(2, 8), torch.zeros(4, 8), torch.zeros(4, 64, dtype=torch.bfloat16),
+                                 torch.zeros(4), 2, 0)

@@ -337,3 +337,26 @@ def test_retrieval_pipeline_matches_encode_then_search_oracle(method):
         assert np.allclose([s for _, s in got[b]], rs[0], atol=1e-5)
     one = pipe.retrieve(batch[0], k)
     assert [p for p, _ in one] == [p for p, _ in got[0]]
+
+
+def test_torch_ops_build_search_exact():
+    """The search is also reachable as torch.ops.tt.* (CUDA only): build -> search -> exact agree with the oracle."""
+    import two_tower_model_v2_b200  # noqa: F401  (registers the ops)
+    from two_tower_model_v2_b200 import _native
+    rng = np.random.default_rng(31)
+    N, D, nq, k = 50000, 96, 21, 10
+    x = rng.standard_normal((N, D)).astype(np.float32)
+    q = rng.standard_normal((nq, D)).astype(np.float32)
+    xd = torch.from_numpy(x).to(dev())
+    xn = torch.empty_like(xd)
+    xh = torch.empty((N, int(_native.load().tt_flat_pitch(D))), device=dev(), dtype=torch.bfloat16)
+    stats = torch.zeros(4, device=dev())
+    torch.ops.tt.flat_build(xd, xn, xh, stats, 0, True)
+    s, i, flags, nunc = torch.ops.tt.flat_search(torch.from_numpy(q).to(dev()), xn, xh, stats, k, 0)
+    assert int(nunc.item()) == 0 and bool((flags == 1).all())
+    es, ei = torch.ops.tt.flat_search_exact(torch.from_numpy(q).to(dev()), xn, k, 0)
+    assert torch.equal(i, ei) and (s - es).abs().max().item() <= 1e-6
+    xnn, qn = fo.normalize_rows(x), fo.normalize_rows(q)
+    rs, ri = fo.search(xnn, qn, k)
+    ok, msg = fo.compare_topk(s.cpu().numpy(), i.cpu().numpy(), rs, ri, xnn, qn)
+    assert ok, msg

@@ -151,3 +151,41 @@ def test_retrieval_pipeline_history_encoding():
     assert idx.tolist() == [[1, 2, -1], [1, 0, -1], [-1, -1, -1]]       # sorted, truncated to the last 3; unsorted; empty
     assert w.tolist() == [[5.0, 10.0, 10.0], [1.0, 1.0, 0.0], [0.0, 0.0, 0.0]]
     assert unknown == 1 and idx.dtype.name == "int64" and w.dtype.name == "float32"
+
+
+def test_micro_batcher_groups_requests_and_truncates_k():
+    import threading
+    from two_tower_model_v2_b200 import MicroBatcher
+    calls = []
+
+    def batch_fn(payloads, k):
+        calls.append((list(payloads), k))
+        return [[(f"{p}-{j}", 1.0 - 0.01 * j) for j in range(k)] for p in payloads]
+
+    with MicroBatcher(batch_fn, max_batch=4, max_wait_ms=200.0) as mb:
+        futs = [mb.submit(f"q{i}", k=3 + (i % 2)) for i in range(4)]         # fills one batch at once
+        res = [f.result(timeout=5) for f in futs]
+        assert [len(r) for r in res] == [3, 4, 3, 4] and res[1][0][0] == "q1-0"
+        assert len(calls) == 1 and calls[0] == (["q0", "q1", "q2", "q3"], 4)  # one call, largest k
+        out = []
+        ts = [threading.Thread(target=lambda i=i: out.append(mb(f"t{i}", 2))) for i in range(6)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert len(out) == 6 and all(len(r) == 2 for r in out)
+        assert mb.requests == 10 and 2 <= mb.batches <= 7 and max(len(c[0]) for c in calls) <= 4
+
+
+def test_micro_batcher_propagates_errors_and_closes():
+    import pytest
+    from two_tower_model_v2_b200 import MicroBatcher
+
+    def bad(payloads, k):
+        raise ValueError("index not built")
+    mb = MicroBatcher(bad, max_batch=8, max_wait_ms=1.0)
+    f1, f2 = mb.submit("a"), mb.submit("b")
+    for f in (f1, f2):
+        with pytest.raises(ValueError):
+            f.result(timeout=5)
+    mb.close()
+    with pytest.raises(RuntimeError):
+        mb.submit("c")

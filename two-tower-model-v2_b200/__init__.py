@@ -10,11 +10,12 @@ CUDA kernels behind the C-ABI in include/tt_b200.h:
 The directory is named `two-tower-model-v2_b200`; import it as `two_tower_model_v2_b200`
 (the root-level `two_tower_model_v2_b200.py` aliases it).
 """
+from .batcher import MicroBatcher
 from .buyer_tower import BuyerTower
 from .config import get_event_weight
 from .retrieval import RetrievalPipeline
 from .sharded import ShardedFlatIPIndex, shard_bounds
 from .vector_db import FlatIPIndex, VectorDatabase, read_flat_ip_file, write_flat_ip_file
 
-__all__ = ["BuyerTower", "VectorDatabase", "FlatIPIndex", "ShardedFlatIPIndex", "RetrievalPipeline", "shard_bounds",
+__all__ = ["BuyerTower", "VectorDatabase", "FlatIPIndex", "ShardedFlatIPIndex", "RetrievalPipeline", "MicroBatcher", "shard_bounds",
            "get_event_weight", "read_flat_ip_file", "write_flat_ip_file"]

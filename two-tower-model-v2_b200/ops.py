@@ -99,6 +99,55 @@ def topk_merge(scores_g: torch.Tensor, ids_g: torch.Tensor) -> Tuple[torch.Tenso
     return scores, ids
 
 
+@torch.library.custom_op("tt::flat_build", mutates_args=("xn", "xh", "stats"), device_types="cuda")
+def flat_build(x: torch.Tensor, xn: torch.Tensor, xh: torch.Tensor, stats: torch.Tensor, row0: int,
+               normalize: bool) -> None:
+    """vector_db.py:44-54 — rows of x -> xn[row0:] (f32, x/(||x||+1e-8) if normalize) and xh[row0:] (bf16 shadow);
+    folds the error-bound norms into stats f32[4].  x may alias xn[row0:row0+rows]."""
+    rows, D = x.shape
+    with torch.cuda.device(x.device):
+        _native.check(_native.load().tt_flat_build(x.data_ptr(), rows, D, 1 if normalize else 0, xn.data_ptr(),
+                                                   xh.data_ptr(), row0, stats.data_ptr(), _stream()), "tt_flat_build")
+
+
+@torch.library.custom_op("tt::flat_search", mutates_args=(), device_types="cuda")
+def flat_search(q: torch.Tensor, xn: torch.Tensor, xh: torch.Tensor, stats: torch.Tensor, k: int,
+                id_offset: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """vector_db.py:152-160 / :189-197 — exact top-k of q f32 [nq,D] (un-normalised) against the index arrays ->
+    (scores f32 [nq,k], ids i64 [nq,k], flags i32 [nq], n_uncertified i32 [1]); rows with flags != 1 must be
+    re-run through tt::flat_search_exact (FlatIPIndex.search_checked_device does both)."""
+    nq, D = q.shape
+    N = xn.shape[0]
+    lib = _native.load()
+    dev = q.device
+    scores = torch.empty((nq, k), device=dev, dtype=torch.float32)
+    ids = torch.empty((nq, k), device=dev, dtype=torch.int64)
+    flags = torch.empty((max(nq, 1),), device=dev, dtype=torch.int32)
+    nunc = torch.empty((1,), device=dev, dtype=torch.int32)
+    ws = torch.empty(max(int(lib.tt_flat_search_workspace_bytes(N, D, max(nq, 1), k)), 256), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _native.check(lib.tt_flat_search(q.data_ptr(), nq, xn.data_ptr(), xh.data_ptr(), stats.data_ptr(), N, D, k, id_offset,
+                                         scores.data_ptr(), ids.data_ptr(), flags.data_ptr(), nunc.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), _stream()), "tt_flat_search")
+    return scores, ids, flags[:nq].clone(), nunc
+
+
+@torch.library.custom_op("tt::flat_search_exact", mutates_args=(), device_types="cuda")
+def flat_search_exact(q: torch.Tensor, xn: torch.Tensor, k: int, id_offset: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Always-exact fp32 path (CUDA-core scoring + radix select) for every row of q."""
+    nq, D = q.shape
+    N = xn.shape[0]
+    lib = _native.load()
+    dev = q.device
+    scores = torch.empty((nq, k), device=dev, dtype=torch.float32)
+    ids = torch.empty((nq, k), device=dev, dtype=torch.int64)
+    ws = torch.empty(max(int(lib.tt_flat_search_exact_workspace_bytes(N, D, nq, k)), 256), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _native.check(lib.tt_flat_search_exact(q.data_ptr(), nq, 0, nq, xn.data_ptr(), N, D, k, id_offset, scores.data_ptr(),
+                                               ids.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "tt_flat_search_exact")
+    return scores, ids
+
+
 def shard_merge(gathered: torch.Tensor, off_scores: int, off_ids: int, off_bound: int, off_flags: int, nq: int, K: int,
                 nunc: torch.Tensor = None):
     """[G, record bytes] all-gathered shard records -> (scores [nq,K], ids [nq,K], flags [nq], n_uncertified [1])
@@ -118,5 +167,5 @@ def shard_merge(gathered: torch.Tensor, off_scores: int, off_ids: int, off_bound
     return scores, ids, flags[:nq], nunc
 
 
-__all__ = ["shard_merge", "pool_weighted", "pool_weighted_gather", "attention_logits", "pool_attention",
+__all__ = ["shard_merge", "flat_build", "flat_search", "flat_search_exact", "pool_weighted", "pool_weighted_gather", "attention_logits", "pool_attention",
            "pool_attention_gather", "topk_merge", "_f32c", "_stream"]
