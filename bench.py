@@ -450,6 +450,7 @@ def main():
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
+            sharded.close()
             dist.destroy_process_group()
         return
 
@@ -471,6 +472,7 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
+        sharded.close()
         dist.destroy_process_group()
 
 

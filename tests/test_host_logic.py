@@ -189,3 +189,56 @@ def test_micro_batcher_propagates_errors_and_closes():
     mb.close()
     with pytest.raises(RuntimeError):
         mb.submit("c")
+
+
+def test_search_planner_properties_random_shapes():
+    """Property test of the host planner over random (N, D, nq, K): shared-memory budget, ring depth, capacities and
+    workspace sizes stay consistent for shapes no example-based test covers."""
+    from hypothesis import given, settings, strategies as st
+    from two_tower_model_v2_b200 import _native
+    lib = _native.load()
+
+    @settings(max_examples=300, deadline=None)
+    @given(N=st.one_of(st.integers(1, 5000), st.integers(5000, 200_000_000)), D=st.integers(1, 1024),
+           nq=st.integers(1, 8192), K=st.integers(1, 2048))
+    def check(N, D, nq, K):
+        K = min(K, N)
+        p = _plan(N, D, nq, K)
+        assert p["k_blocks"] == -(-D // 64) and p["tiles"] == -(-N // 256)
+        if not p["supported"]:
+            assert D > 512                                   # only very wide rows may be rejected
+            return
+        assert p["smem"] <= 227 * 1024 and p["stages"] >= 2 and p["stages"] <= 8
+        assert p["unit_queries"] in (64, 128, 256)
+        assert (p["unit_queries"] == 256) == (nq > 128)
+        assert p["query_units"] * p["unit_queries"] >= nq
+        assert 1 <= p["main_slices"] <= max(p["tiles"], 1) and p["main_slices"] <= 1024
+        ws = lib.tt_flat_search_workspace_bytes(N, D, nq, K)
+        assert ws > 0
+        if p["route_exact"]:
+            assert not p["use_threshold"] and N > 16384
+            return
+        assert p["seg_cap"] >= 1 and p["cap"] <= 16384
+        if p["use_threshold"]:
+            assert p["slots"] >= 1 and p["stride"] >= 1 and p["rank"] >= 1 and p["target"] >= K
+            assert p["slots"] <= 4096 and (p["slots"] - 1) * p["stride"] < p["tiles"]
+            assert p["cap"] >= min(4 * p["target"], 16384) or p["cap"] == 16384
+        else:
+            assert N <= 16384 and p["seg_cap"] * p["main_slices"] >= N     # every row can be a candidate
+        # candidate segments fit the workspace the ABI asks for
+        assert ws >= nq * p["main_slices"] * p["seg_cap"] * 8
+    check()
+
+
+def test_shard_plan_decision_is_rank_independent():
+    """tt_flat_shard_plan_ok depends on (N_total, D, nq, K) and on N_local >= K only: every rank decides alike."""
+    from two_tower_model_v2_b200 import _native
+    lib = _native.load()
+    for n_total, d, nq, k in [(10_000_000, 384, 4096, 100), (10_000_000, 768, 1, 10), (3_000_000, 64, 200, 100),
+                              (1_000_000, 384, 300, 100), (50_000, 32, 8, 10)]:
+        decisions = {lib.tt_flat_shard_plan_ok(nl, n_total, d, nq, k) for nl in (k, 1000 + k, n_total // 8, n_total // 2)}
+        assert len(decisions) == 1, (n_total, d, nq, k, decisions)
+        assert lib.tt_flat_shard_plan_ok(max(k - 1, 1), n_total, d, nq, k) == (0 if k > 1 else decisions.pop())
+    assert lib.tt_flat_shard_plan_ok(1_250_000, 10_000_000, 384, 4096, 100) == 1      # the benchmarked configuration
+    assert lib.tt_flat_shard_workspace_bytes(1_250_000, 10_000_000, 384, 4096, 100) > 0
+    assert lib.tt_flat_shard_plan_ok(125_000, 1_000_000, 384, 300, 100) == 0          # 1M rows: chunk-mode sample

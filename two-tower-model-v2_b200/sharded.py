@@ -136,6 +136,23 @@ class P2PExchange:
         self._ptr_arrays = {}
         dist.barrier(group=group)       # every rank has mapped every buffer before the first push
 
+    def close(self) -> None:
+        """Collective: every rank calls it after its last exchange.  Order matters for CUDA IPC: all ranks finish
+        their work, every rank unmaps the peers' buffers, and only then does anybody free its own buffer."""
+        if getattr(self, "base", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for r, p in enumerate(self.peer_base):
+                if r != self.rank:
+                    self.lib.tt_p2p_close(self._ctypes.c_void_p(p))
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            self.buf = None
+            self.lib.tt_p2p_free(self._ctypes.c_void_p(self.base))
+        self.base, self.peer_base = None, []
+
     def _ptrs(self, ch: int, parity: int):
         key = (ch, parity)
         arr = self._ptr_arrays.get(key)
@@ -208,6 +225,13 @@ class ShardedFlatIPIndex:
             gathered[0].copy_(rec)
         else:
             dist.all_gather_into_tensor(gathered.view(-1), rec, group=self.group)
+
+    def close(self) -> None:
+        """Releases the peer-memory exchanges (every rank, after its last search has completed)."""
+        for ex in self._p2p.values():
+            if ex is not None:
+                ex.close()
+        self._p2p.clear()
 
     def _p2p_for(self, nq: int, k: int, device, world: int, lay: RecordLayout):
         """The P2PExchange for this (nq, k) shape (channel 0: top-r lists, channel 1: result records), or None

@@ -60,7 +60,7 @@ class _FlagRing:
     copied into one of them asynchronously, so the host can look at them later without draining the stream."""
     WIDTH = 2
 
-    def __init__(self, n: int = 16):
+    def __init__(self, n: int = 64):     # more searches than this in flight would recycle a slot
         self.host = torch.zeros((n, self.WIDTH), dtype=torch.int32, pin_memory=True)
         self.n, self.next = n, 0
 
