@@ -8,7 +8,10 @@
 // (fma.rn.f32x2, two k-partial sums per 64-bit accumulator): half the issue slots per FMA, which is
 // what the unpacked version was short of (ncu: 70 % issue utilisation, 24 % dispatch stalls at 52 % of
 // the FMA peak).
+#include <stdlib.h>
+#include <string.h>
 #include "tt_common.cuh"
+#include "flat_internal.cuh"
 
 namespace tt {
 
@@ -179,6 +182,13 @@ extern "C" __attribute__((visibility("default"))) int tt_attention_logits(const 
   cudaStream_t st = (cudaStream_t)stream;
   const bool fast = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(W1) & 15) == 0);
+  // Tensor-core path (3xTF32, fp32-accurate) for aligned shapes with H <= 256; TT_B200_ATTN_LOGITS=fma keeps the
+  // CUDA-core FFMA2 kernel.
+  static const bool want_tc = [] { const char* e = getenv("TT_B200_ATTN_LOGITS"); return !(e && strcmp(e, "fma") == 0); }();
+  if (fast && want_tc && R >= 128) {
+    const int e = launch_attn_logits_tc(x, R, D, W1, b1, W2, b2, H, logits, st);
+    if (e != TT_ERR_UNSUPPORTED) return e;
+  }
   if (fast) {
     const size_t smem = 2 * AL_STAGE_FLOATS * sizeof(float);
     TT_CHECK_CUDA(cudaFuncSetAttribute(attn_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -53,6 +53,11 @@ int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long l
                     const void* cand, float* scores, long long* ids, int* flags, int* n_uncertified,
                     float* bound_out, cudaStream_t st);
 
+// shared TMA descriptor helper (flat_scan.cu) and the tensor-core attention-logits launcher (attn_logits_tc.cu)
+int make_tmap_f32(void* tensor_map /* CUtensorMap* */, const void* base, long long rows, int cols, int box_rows, int box_cols);
+int launch_attn_logits_tc(const float* x, long long R, int D, const float* W1, const float* b1, const float* W2,
+                          const float* b2, int H, float* logits, cudaStream_t st);
+
 // Optional device-side timing of the main scan kernel (bench.py roofline): when armed, launch_scan
 // brackets the main scan launch with a pair of CUDA events on the launching stream.
 void profile_scan_begin(cudaStream_t st);

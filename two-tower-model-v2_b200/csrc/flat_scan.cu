@@ -609,6 +609,26 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, int 
   return TT_OK;
 }
 
+// fp32 [rows, cols] row-major (row pitch = cols*4 bytes, a multiple of 16), box = [box_rows, box_cols <= 32],
+// 128-byte swizzle, out-of-range rows/columns read as 0.
+int make_tmap_f32(void* tensor_map, const void* base, long long rows, int cols, int box_rows, int box_cols) {
+  CUtensorMap* m = reinterpret_cast<CUtensorMap*>(tensor_map);
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return TT_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (f32) failed with CUresult " + std::to_string((int)r));
+    return TT_ERR_CUDA;
+  }
+  return TT_OK;
+}
+
 // Number of catalog slices for `nqu` query units on `cap` concurrent units (SMs, or SM pairs):
 // the count that wastes the fewest unit slots over whole waves.
 static int pick_slices(int nqu, int cap, int max_slices) {
