@@ -6,14 +6,16 @@
 // and  x.w ~= xb.wb + xb.ws + xs.wb  (the dropped xs.ws term is ~2^-22 relative), accumulated in fp32 in TMEM
 // by tcgen05.mma kind::tf32.  Error vs fp32 FMA arithmetic: ~1e-7 relative, the same order as fp32 itself.
 //
-// CTA = one 128-row tile of x, 256 threads:
-//   warp 0 lane 0 : TMA producer - per 32-column K-block the raw fp32 tiles x[128 x 32] and W1[Hp x 32]
-//                   (128-byte rows, 128B swizzle) into a 3-stage ring
-//   warps 4-7     : splitters - rewrite each landed tile in place as `big` and write `small` next to it
-//                   (same swizzled offsets), fence.proxy.async, arrive; after the last K-block they turn into
-//                   the epilogue: tcgen05.ld the [128 x Hp] hidden pre-activations, relu(.+b1).W2 + b2
-//   warp 1 lane 0 : MMA issuer - 4 K=8 steps x 3 MMAs per K-block, M = 128, N = Hp
-//   warp 2        : TMEM allocator
+// Persistent CTAs (one per SM, 384 threads) loop over 128-row tiles of x:
+//   warp 0 lane 0     : TMA producer - per 32-column K-block the raw fp32 tiles x[128 x 32] and W1[Hp x 32]
+//                       (128-byte rows, 128B swizzle) into a 3-stage ring
+//   warps 2,3,8-11    : splitters - rewrite each landed tile in place as `big` and write `small` next to it
+//                       (same swizzled offsets), fence.proxy.async, arrive
+//   warp 1 lane 0     : MMA issuer - 4 K=8 steps x 3 MMAs per K-block, M = 128, N = Hp, accumulators
+//                       double-buffered in TMEM (2 x Hp columns)
+//   warps 4-7         : epilogue - tcgen05.ld the [128 x Hp] hidden pre-activations of the finished tile,
+//                       relu(.+b1).W2 + b2, one row per thread; overlaps the next tile's MMAs
+//   warp 2            : also the TMEM allocator
 // Rooflines: tf32 tensor pipe (3 x 2*D*Hp flop per row at half the bf16 rate) and shared-memory bandwidth
 // (every MMA streams both operands from shared memory; the splitters add one read and two writes per tile).
 #include <cuda.h>
@@ -27,7 +29,8 @@ using namespace ptx;
 
 constexpr int TC_BM = 128;          // rows per CTA
 constexpr int TC_BK = 32;           // fp32 per K-block = one 128-byte swizzle row
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;
+constexpr int TC_SPLIT_WARPS = 6;
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_X_TILE = TC_BM * TC_BK * 4;   // 16 KB
 
@@ -38,6 +41,7 @@ struct AttnTcParams {
   int num_stages;
   int stage_bytes;    // 2 x-tiles + 2 W-tiles
   int tmem_cols;
+  int num_tiles;
   const float* b1;
   const float* W2;
   const float* b2;
@@ -65,14 +69,31 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
-// In place: tile -> big, small written at the same offsets of `small_tile`.  16-byte chunks, 128 threads.
+// In place: tile -> big, small written at the same offsets of `small_tile`.  16-byte chunks strided over the
+// TC_SPLIT_WARPS*32 splitter threads, four chunks in flight per thread.
+__device__ __forceinline__ void split_chunk(const float4 v, uint4& b, uint4& s) {
+  b.x = rna_tf32(v.x); b.y = rna_tf32(v.y); b.z = rna_tf32(v.z); b.w = rna_tf32(v.w);
+  s.x = rna_tf32(v.x - __uint_as_float(b.x)); s.y = rna_tf32(v.y - __uint_as_float(b.y));
+  s.z = rna_tf32(v.z - __uint_as_float(b.z)); s.w = rna_tf32(v.w - __uint_as_float(b.w));
+}
 __device__ __forceinline__ void split_tile(uint8_t* tile, uint8_t* small_tile, int bytes, int t) {
-  for (int off = t * 16; off < bytes; off += 128 * 16) {
-    const float4 v = *reinterpret_cast<const float4*>(tile + off);
+  constexpr int STEP = TC_SPLIT_WARPS * 32 * 16;
+  int off = t * 16;
+  for (; off + 3 * STEP < bytes; off += 4 * STEP) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(tile + off + u * STEP);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint4 b, s;
+      split_chunk(v[u], b, s);
+      *reinterpret_cast<uint4*>(tile + off + u * STEP) = b;
+      *reinterpret_cast<uint4*>(small_tile + off + u * STEP) = s;
+    }
+  }
+  for (; off < bytes; off += STEP) {
     uint4 b, s;
-    b.x = rna_tf32(v.x); b.y = rna_tf32(v.y); b.z = rna_tf32(v.z); b.w = rna_tf32(v.w);
-    s.x = rna_tf32(v.x - __uint_as_float(b.x)); s.y = rna_tf32(v.y - __uint_as_float(b.y));
-    s.z = rna_tf32(v.z - __uint_as_float(b.z)); s.w = rna_tf32(v.w - __uint_as_float(b.w));
+    split_chunk(*reinterpret_cast<const float4*>(tile + off), b, s);
     *reinterpret_cast<uint4*>(tile + off) = b;
     *reinterpret_cast<uint4*>(small_tile + off) = s;
   }
@@ -86,22 +107,26 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   const int w_tile = p.Hp * TC_BK * 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * p.stage_bytes);
   uint64_t* full_bar = bars;                          // [TC_MAX_STAGES]  TMA landed
-  uint64_t* split_bar = bars + TC_MAX_STAGES;         // [TC_MAX_STAGES]  big/small written (4 warp arrivals)
+  uint64_t* split_bar = bars + TC_MAX_STAGES;         // [TC_MAX_STAGES]  big/small written (one arrival per splitter warp)
   uint64_t* empty_bar = bars + 2 * TC_MAX_STAGES;     // [TC_MAX_STAGES]  MMAs of the stage retired
-  uint64_t* tmem_full_bar = bars + 3 * TC_MAX_STAGES; // [1]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = bars + 3 * TC_MAX_STAGES; // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]  one arrival per epilogue warp
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row0 = (long long)blockIdx.x * TC_BM;
+  const int my_tiles = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_x); prefetch_tensormap(&tmap_w); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.num_stages; ++i) {
       mbar_init(smem_u32(full_bar + i), 1);
-      mbar_init(smem_u32(split_bar + i), 4);
+      mbar_init(smem_u32(split_bar + i), TC_SPLIT_WARPS);
       mbar_init(smem_u32(empty_bar + i), 1);
     }
-    mbar_init(smem_u32(tmem_full_bar), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(tmem_full_bar + i), 1);
+      mbar_init(smem_u32(tmem_empty_bar + i), 4);
+    }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(smem_u32(tmem_ptr_smem), (uint32_t)p.tmem_cols); tmem_relinquish(); }
@@ -109,19 +134,23 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const bool splitter = (warp == 2 || warp == 3 || warp >= 8);
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(smem_u32(empty_bar + stage), phase ^ 1, 400 + stage);
-        const uint32_t fb = smem_u32(full_bar + stage);
-        uint8_t* st = smem + (size_t)stage * p.stage_bytes;
-        mbar_arrive_expect_tx(fb, (uint32_t)(TC_X_TILE + w_tile));
-        tma_load_2d(smem_u32(st), &tmap_x, fb, kb * TC_BK, (int)row0);                     // x big (raw for now)
-        tma_load_2d(smem_u32(st + 2 * TC_X_TILE), &tmap_w, fb, kb * TC_BK, 0);             // W big (raw for now)
-        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      for (int i = 0; i < my_tiles; ++i) {
+        const long long row0 = (long long)((int)blockIdx.x + i * (int)gridDim.x) * TC_BM;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1, 400 + stage);
+          const uint32_t fb = smem_u32(full_bar + stage);
+          uint8_t* st = smem + (size_t)stage * p.stage_bytes;
+          mbar_arrive_expect_tx(fb, (uint32_t)(TC_X_TILE + w_tile));
+          tma_load_2d(smem_u32(st), &tmap_x, fb, kb * TC_BK, (int)row0);                     // x big (raw for now)
+          tma_load_2d(smem_u32(st + 2 * TC_X_TILE), &tmap_w, fb, kb * TC_BK, 0);             // W big (raw for now)
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
     __syncwarp();
@@ -130,33 +159,39 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       const uint32_t idesc = make_idesc_tf32_f32(TC_BM, p.Hp);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(smem_u32(split_bar + stage), phase, 410 + stage);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int buf = i & 1;
+        mbar_wait(smem_u32(tmem_empty_bar + buf), (((uint32_t)i >> 1) & 1u) ^ 1u, 440 + buf);
         tc_fence_after();
-        uint8_t* st = smem + (size_t)stage * p.stage_bytes;
-        const uint64_t xb = make_smem_desc_sw128(smem_u32(st));
-        const uint64_t xs = make_smem_desc_sw128(smem_u32(st + TC_X_TILE));
-        const uint64_t wb = make_smem_desc_sw128(smem_u32(st + 2 * TC_X_TILE));
-        const uint64_t ws = make_smem_desc_sw128(smem_u32(st + 2 * TC_X_TILE + w_tile));
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.Hp);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(split_bar + stage), phase, 410 + stage);
+          tc_fence_after();
+          uint8_t* st = smem + (size_t)stage * p.stage_bytes;
+          const uint64_t xb = make_smem_desc_sw128(smem_u32(st));
+          const uint64_t xs = make_smem_desc_sw128(smem_u32(st + TC_X_TILE));
+          const uint64_t wb = make_smem_desc_sw128(smem_u32(st + 2 * TC_X_TILE));
+          const uint64_t ws = make_smem_desc_sw128(smem_u32(st + 2 * TC_X_TILE + w_tile));
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);       // 32 bytes per K = 8 step
-          mma_tf32_ss(tmem_base, xb + koff, wb + koff, idesc, (uint32_t)((kb | k) != 0));
-          mma_tf32_ss(tmem_base, xb + koff, ws + koff, idesc, 1u);
-          mma_tf32_ss(tmem_base, xs + koff, wb + koff, idesc, 1u);
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);       // 32 bytes per K = 8 step
+            mma_tf32_ss(d_tmem, xb + koff, wb + koff, idesc, (uint32_t)((kb | k) != 0));
+            mma_tf32_ss(d_tmem, xb + koff, ws + koff, idesc, 1u);
+            mma_tf32_ss(d_tmem, xs + koff, wb + koff, idesc, 1u);
+          }
+          mma_commit(smem_u32(empty_bar + stage));
+          if (kb == p.num_kb - 1) mma_commit(smem_u32(tmem_full_bar + buf));
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
-        mma_commit(smem_u32(empty_bar + stage));
-        if (kb == p.num_kb - 1) mma_commit(smem_u32(tmem_full_bar));
-        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ---- splitters ------------------------------------------------------------------------------
-    const int t = threadIdx.x - 128;
+  } else if (splitter) {
+    const int sw = (warp < 4) ? warp - 2 : warp - 6;          // 0..5
+    const int t = sw * 32 + lane;
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = 0; kb < p.num_kb; ++kb) {
+    for (int n = 0; n < my_tiles * p.num_kb; ++n) {
       mbar_wait(smem_u32(full_bar + stage), phase, 420 + stage);
       uint8_t* st = smem + (size_t)stage * p.stage_bytes;
       split_tile(st, st + TC_X_TILE, TC_X_TILE, t);
@@ -166,25 +201,33 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       if (lane == 0) mbar_arrive(smem_u32(split_bar + stage));
       if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
     }
-    // ---- epilogue: one row per thread -----------------------------------------------------------
+  } else {
+    // ---- epilogue (warps 4-7): one row per thread ---------------------------------------------------
     const int quad = warp & 3;
-    mbar_wait(smem_u32(tmem_full_bar), 0, 430);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    float logit = 0.f;
-    for (int c = 0; c < p.Hp; c += 32) {
-      uint32_t v[32];
-      __syncwarp();
-      tmem_ld_32x32(taddr + (uint32_t)c, v);
-      tmem_ld_wait();
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i & 1;
+      const long long row0 = (long long)((int)blockIdx.x + i * (int)gridDim.x) * TC_BM;
+      mbar_wait(smem_u32(tmem_full_bar + buf), ((uint32_t)i >> 1) & 1u, 430 + buf);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.Hp);
+      float logit = 0.f;
+      for (int c = 0; c < p.Hp; c += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_32x32(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int h = c + j;
-        if (h < p.H) logit = fmaf(fmaxf(__uint_as_float(v[j]) + __ldg(p.b1 + h), 0.f), __ldg(p.W2 + h), logit);
+        for (int j = 0; j < 32; ++j) {
+          const int h = c + j;
+          if (h < p.H) logit = fmaf(fmaxf(__uint_as_float(v[j]) + __ldg(p.b1 + h), 0.f), __ldg(p.W2 + h), logit);
+        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty_bar + buf));
+      const long long r = row0 + quad * 32 + lane;
+      if (r < p.R) p.logits[r] = logit + __ldg(p.b2);
     }
-    const long long r = row0 + quad * 32 + lane;
-    if (r < p.R) p.logits[r] = logit + __ldg(p.b2);
   }
 
   tc_fence_before();
@@ -206,14 +249,15 @@ int launch_attn_logits_tc(const float* x, long long R, int D, const float* W1, c
   if (p.num_stages > TC_MAX_STAGES) p.num_stages = TC_MAX_STAGES;
   if (p.num_stages < 2) return TT_ERR_UNSUPPORTED;
   p.tmem_cols = 32;
-  while (p.tmem_cols < Hp) p.tmem_cols <<= 1;
+  while (p.tmem_cols < 2 * Hp) p.tmem_cols <<= 1;      // two accumulator buffers
   p.b1 = b1; p.W2 = W2; p.b2 = b2; p.logits = logits;
   CUtensorMap tx, tw;
   if (int e = make_tmap_f32(&tx, x, R, D, TC_BM, TC_BK)) return e;
   if (int e = make_tmap_f32(&tw, W1, H, D, Hp, TC_BK)) return e;
   const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256;
   TT_CHECK_CUDA(cudaFuncSetAttribute(attn_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long grid = (R + TC_BM - 1) / TC_BM;
+  p.num_tiles = (int)((R + TC_BM - 1) / TC_BM);
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   attn_logits_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, st>>>(tx, tw, p);
   TT_CHECK_LAUNCH();
   return TT_OK;
