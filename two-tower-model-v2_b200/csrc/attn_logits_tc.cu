@@ -7,10 +7,10 @@
 // by tcgen05.mma kind::tf32.  Error vs fp32 FMA arithmetic: ~1e-7 relative, the same order as fp32 itself.
 //
 // Persistent CTAs (one per SM, 384 threads) loop over 128-row tiles of x:
-//   warp 0 lane 0     : TMA producer - per 32-column K-block the raw fp32 tiles x[128 x 32] and W1[Hp x 32]
+//   warp 0 lane 0     : TMA producer - per 32-column K-block the raw fp32 tile x[128 x 32] and the big/small W1[Hp x 32]
 //                       (128-byte rows, 128B swizzle) into a 3-stage ring
-//   warps 2,3,8-11    : splitters - rewrite each landed tile in place as `big` and write `small` next to it
-//                       (same swizzled offsets), fence.proxy.async, arrive
+//   warps 2,3,8-11    : splitters - rewrite each landed x tile in place as `big` and write `small` next to it
+//                       (same swizzled offsets), fence.proxy.async, arrive (W1 is pre-split once per call)
 //   warp 1 lane 0     : MMA issuer - 4 K=8 steps x 3 MMAs per K-block, M = 128, N = Hp, accumulators
 //                       double-buffered in TMEM (2 x Hp columns)
 //   warps 4-7         : epilogue - tcgen05.ld the [128 x Hp] hidden pre-activations of the finished tile,
@@ -19,6 +19,7 @@
 // Rooflines: tf32 tensor pipe (3 x 2*D*Hp flop per row at half the bf16 rate) and shared-memory bandwidth
 // (every MMA streams both operands from shared memory; the splitters add one read and two writes per tile).
 #include <cuda.h>
+#include <mutex>
 #include "tt_common.cuh"
 #include "sm100_ptx.cuh"
 #include "flat_internal.cuh"
@@ -146,9 +147,10 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1, 400 + stage);
           const uint32_t fb = smem_u32(full_bar + stage);
           uint8_t* st = smem + (size_t)stage * p.stage_bytes;
-          mbar_arrive_expect_tx(fb, (uint32_t)(TC_X_TILE + w_tile));
-          tma_load_2d(smem_u32(st), &tmap_x, fb, kb * TC_BK, (int)row0);                     // x big (raw for now)
-          tma_load_2d(smem_u32(st + 2 * TC_X_TILE), &tmap_w, fb, kb * TC_BK, 0);             // W big (raw for now)
+          mbar_arrive_expect_tx(fb, (uint32_t)(TC_X_TILE + 2 * w_tile));
+          tma_load_2d(smem_u32(st), &tmap_x, fb, kb * TC_BK, (int)row0);                     // x raw (split in place)
+          tma_load_2d(smem_u32(st + 2 * TC_X_TILE), &tmap_w, fb, kb * TC_BK, 0);             // W big  (pre-split)
+          tma_load_2d(smem_u32(st + 2 * TC_X_TILE + w_tile), &tmap_w, fb, kb * TC_BK, p.Hp); // W small
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -195,7 +197,6 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       mbar_wait(smem_u32(full_bar + stage), phase, 420 + stage);
       uint8_t* st = smem + (size_t)stage * p.stage_bytes;
       split_tile(st, st + TC_X_TILE, TC_X_TILE, t);
-      split_tile(st + 2 * TC_X_TILE, st + 2 * TC_X_TILE + w_tile, w_tile, t);
       fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(split_bar + stage));
@@ -235,6 +236,40 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
+// W1 f32 [H, D] -> Wsplit f32 [2][Hp][D]: big = rna_tf32(w), small = rna_tf32(w - big); rows >= H are zero.
+// Done once per call (the same weights serve every row tile).
+__global__ void attn_split_w_kernel(const float* __restrict__ W1, int H, int Hp, int D, float* __restrict__ out) {
+  const long long n = (long long)Hp * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(i / D);
+    const float w = (h < H) ? W1[i] : 0.f;
+    const uint32_t b = rna_tf32(w);
+    out[i] = __uint_as_float(b);
+    out[n + i] = __uint_as_float(rna_tf32(w - __uint_as_float(b)));
+  }
+}
+
+// Library-private stream-ordered memory pool (one per device) for the split weights: blocks are reused across
+// calls instead of going back to the driver at every synchronisation (the default pool's behaviour).
+static cudaMemPool_t scratch_pool(int dev) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    unsigned long long keep = ~0ull;
+    (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    pools[dev] = pool;
+  }
+  return pools[dev];
+}
+
 // Returns TT_ERR_UNSUPPORTED (without setting an error) when the shape does not fit this kernel.
 int launch_attn_logits_tc(const float* x, long long R, int D, const float* W1, const float* b1, const float* W2,
                           const float* b2, int H, float* logits, cudaStream_t st) {
@@ -251,15 +286,27 @@ int launch_attn_logits_tc(const float* x, long long R, int D, const float* W1, c
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * Hp) p.tmem_cols <<= 1;      // two accumulator buffers
   p.b1 = b1; p.W2 = W2; p.b2 = b2; p.logits = logits;
+  // split weights live in a stream-ordered scratch allocation (freed after the kernel on the same stream)
+  float* wsplit = nullptr;
+  int dev = 0;
+  TT_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool = scratch_pool(dev);
+  if (!pool) return TT_ERR_UNSUPPORTED;          // no stream-ordered allocator: the FFMA2 kernel serves the call
+  TT_CHECK_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&wsplit), (size_t)2 * Hp * D * sizeof(float), pool, st));
+  attn_split_w_kernel<<<64, 256, 0, st>>>(W1, H, Hp, D, wsplit);
+  TT_CHECK_LAUNCH();
   CUtensorMap tx, tw;
-  if (int e = make_tmap_f32(&tx, x, R, D, TC_BM, TC_BK)) return e;
-  if (int e = make_tmap_f32(&tw, W1, H, D, Hp, TC_BK)) return e;
+  if (int e = make_tmap_f32(&tx, x, R, D, TC_BM, TC_BK)) { cudaFreeAsync(wsplit, st); return e; }
+  if (int e = make_tmap_f32(&tw, wsplit, 2LL * Hp, D, Hp, TC_BK)) { cudaFreeAsync(wsplit, st); return e; }
   const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256;
   TT_CHECK_CUDA(cudaFuncSetAttribute(attn_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.num_tiles = (int)((R + TC_BM - 1) / TC_BM);
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   attn_logits_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, st>>>(tx, tw, p);
-  TT_CHECK_LAUNCH();
+  count_launch();
+  const cudaError_t le = cudaGetLastError();
+  TT_CHECK_CUDA(cudaFreeAsync(wsplit, st));
+  TT_CHECK_CUDA(le);
   return TT_OK;
 }
 
