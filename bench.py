@@ -297,6 +297,31 @@ def cpu_baseline_search(n_total, d, nq, k, sample_rows=1 << 20, reps=2):
             "seconds_per_sample_step": best, "host_cpus": os.cpu_count()}
 
 
+def cpu_baseline_pooling(buyers=1024, S=50, D=384, H=128, reps=3):
+    """Reported baseline for the second half of the metric (buyer encodes/s): the torch-CPU port of the reference
+    BuyerTower (oracle/buyer_tower_oracle.torch_forward: the same eager ops the reference issues) on a bounded sample of
+    C2, all host threads."""
+    from oracle import buyer_tower_oracle as bo
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn((buyers, S, D), generator=g)
+    w = torch.tensor([1.0, 5.0, 10.0])[torch.multinomial(torch.tensor([0.75, 0.18, 0.07]), buyers * S, True, generator=g)].view(buyers, S)
+    torch.manual_seed(0)
+    l1, l2 = torch.nn.Linear(D, H), torch.nn.Linear(H, 1)
+    params = (l1.weight.detach(), l1.bias.detach(), l2.weight.detach(), l2.bias.detach())
+    out = {"cores": torch.get_num_threads(), "kind": "port",
+           "sample": f"{buyers} of 4096 buyers x {S} events x {D} f32, torch-CPU eager ops of the reference module"}
+    with torch.no_grad():
+        for method in ("weighted_avg", "attention"):
+            bo.torch_forward(x, w, method, params)
+            best = float("inf")
+            for _ in range(reps):
+                t = time.perf_counter()
+                bo.torch_forward(x, w, method, params)
+                best = min(best, time.perf_counter() - t)
+            out[method] = {"buyer_encodes_per_s": buyers / best, "seconds_per_sample": best}
+    return out
+
+
 def run_reference(args):
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -471,6 +496,10 @@ def main():
                              "query_batch_sweep": batch_sweep(index, lib, peaks, n_total, d, k, [1, 128, 1024])}
         line["secondary"]["retrieve_path"] = bench_retrieve_path(index, d, k)
         line["cpu_baseline"] = cpu_baseline_search(n_total, d, nq, k)
+        try:
+            line["secondary"]["pooling"]["cpu_baseline"] = cpu_baseline_pooling()
+        except Exception as e:                       # a reported extra must never cost the headline line
+            line["secondary"]["pooling"]["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
