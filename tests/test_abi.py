@@ -72,3 +72,43 @@ def test_torch_ops_are_cuda_only():
     with pytest.raises(NotImplementedError):
         torch.ops.tt.flat_search(torch.zeros(2, 8), torch.zeros(4, 8), torch.zeros(4, 64, dtype=torch.bfloat16),
                                  torch.zeros(4), 2, 0)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path, native_lib):
+    """include/tt_b200.h must be usable from C (the boundary is a C-ABI): compile a C99 translation unit against it
+    with -Wall -Werror -pedantic, link it to the shared library and run it without a GPU (argument errors and
+    host-only helpers must work; nothing may crash)."""
+    import shutil
+    import subprocess
+    from two_tower_model_v2_b200 import _native
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi_demo.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "tt_b200.h"
+int main(void) {
+  int32_t plan[16];
+  if (tt_abi_version() != TT_B200_ABI_VERSION) return 10;
+  if (tt_flat_pitch(384) != 384 || tt_flat_pitch(1) != 64) return 11;
+  if (tt_pool_weighted(NULL, NULL, NULL, 1, 1, 1, NULL) != TT_ERR_INVALID) return 12;
+  if (strstr(tt_last_error(), "null pointer") == NULL) return 13;
+  if (tt_flat_plan_describe(10000000, 384, 4096, 100, plan) != TT_OK) return 14;
+  if (plan[0] != 1 || plan[1] != 256 || plan[2] != 6) return 15;         /* supported, CTA pairs, 6 K-blocks */
+  if (tt_flat_search_workspace_bytes(10000000, 384, 4096, 100) == 0) return 16;
+  if (tt_flat_shard_plan_ok(1250000, 10000000, 384, 4096, 100) != 1) return 17;
+  if (tt_shard_merge(NULL, 0, 0, 0, 0, 0, 1, 1, 1, NULL, NULL, NULL, NULL, NULL) != TT_ERR_INVALID) return 18;
+  printf("abi ok, TT_FLAT_MAX_K=%d TT_SHARD_TOPR=%d\n", TT_FLAT_MAX_K, TT_SHARD_TOPR);
+  return 0;
+}
+''')
+    exe = tmp_path / "abi_demo"
+    lib = Path(_native.LIB_PATH)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", str(HEADER.parent), str(src), "-o", str(exe),
+                        "-L", str(lib.parent), "-ltt_b200", f"-Wl,-rpath,{lib.parent}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, f"exit {run.returncode}: {run.stdout} {run.stderr}"
+    assert "abi ok" in run.stdout
