@@ -360,3 +360,21 @@ def test_torch_ops_build_search_exact():
     rs, ri = fo.search(xnn, qn, k)
     ok, msg = fo.compare_topk(s.cpu().numpy(), i.cpu().numpy(), rs, ri, xnn, qn)
     assert ok, msg
+
+
+def test_native_shard_save_load_search_identical(tmp_path):
+    """A shard written with save_native and read back with load_native answers bit-identically (no re-normalisation)."""
+    import two_tower_model_v2_b200 as pkg
+    rng = np.random.default_rng(41)
+    x = rng.standard_normal((30000, 100)).astype(np.float32)
+    q = torch.from_numpy(rng.standard_normal((17, 100)).astype(np.float32)).to(dev())
+    idx = build(x)
+    idx.id_offset = 777
+    p = str(tmp_path / "shard.ttb2")
+    idx.save_native(p, n_total=100000)
+    back = pkg.FlatIPIndex.load_native(p)
+    assert back.ntotal == idx.ntotal and back.id_offset == 777
+    assert torch.equal(back.xn, idx.xn) and torch.equal(back.xh.view(torch.int16), idx.xh.view(torch.int16))
+    s1, i1, _ = idx.search_checked_device(q, 10)
+    s2, i2, _ = back.search_checked_device(q, 10)
+    assert torch.equal(s1, s2) and torch.equal(i1, i2) and int(i1.min()) >= 777

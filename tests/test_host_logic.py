@@ -242,3 +242,27 @@ def test_shard_plan_decision_is_rank_independent():
     assert lib.tt_flat_shard_plan_ok(1_250_000, 10_000_000, 384, 4096, 100) == 1      # the benchmarked configuration
     assert lib.tt_flat_shard_workspace_bytes(1_250_000, 10_000_000, 384, 4096, 100) > 0
     assert lib.tt_flat_shard_plan_ok(125_000, 1_000_000, 384, 300, 100) == 0          # 1M rows: chunk-mode sample
+
+
+def test_native_shard_file_roundtrip_and_validation(tmp_path):
+    import pytest
+    from two_tower_model_v2_b200 import read_native_shard, write_native_shard
+    rng = np.random.default_rng(5)
+    rows, d, dp = 37, 100, 128
+    xn = rng.standard_normal((rows, d)).astype(np.float32)
+    xh = rng.integers(0, 65536, (rows, dp), dtype=np.uint16)
+    stats = np.array([1.0007, 0.0021, 0.0, 0.0], np.float32)
+    p = tmp_path / "shard3.ttb2"
+    write_native_shard(str(p), xn, xh, stats, id_offset=1234, n_total=5000)
+    assert p.stat().st_size == 64 + rows * d * 4 + rows * dp * 2
+    gx, gh, gs, off, ntot = read_native_shard(str(p))
+    assert np.array_equal(gx, xn) and np.array_equal(gh, xh) and np.array_equal(gs, stats) and (off, ntot) == (1234, 5000)
+    raw = p.read_bytes()
+    (tmp_path / "cut").write_bytes(raw[:-10])
+    with pytest.raises(ValueError, match="truncated"):
+        read_native_shard(str(tmp_path / "cut"))
+    (tmp_path / "bad").write_bytes(b"X" + raw[1:])
+    with pytest.raises(ValueError, match="not a tt_b200 shard"):
+        read_native_shard(str(tmp_path / "bad"))
+    with pytest.raises(ValueError, match="pitch"):
+        write_native_shard(str(tmp_path / "x"), xn, xh[:, :100], stats)

@@ -15,7 +15,8 @@ from .buyer_tower import BuyerTower
 from .config import get_event_weight
 from .retrieval import RetrievalPipeline
 from .sharded import ShardedFlatIPIndex, shard_bounds
-from .vector_db import FlatIPIndex, VectorDatabase, read_flat_ip_file, write_flat_ip_file
+from .vector_db import (FlatIPIndex, VectorDatabase, read_flat_ip_file, read_native_shard, write_flat_ip_file,
+                        write_native_shard)
 
 __all__ = ["BuyerTower", "VectorDatabase", "FlatIPIndex", "ShardedFlatIPIndex", "RetrievalPipeline", "MicroBatcher", "shard_bounds",
-           "get_event_weight", "read_flat_ip_file", "write_flat_ip_file"]
+           "get_event_weight", "read_flat_ip_file", "write_flat_ip_file", "read_native_shard", "write_native_shard"]

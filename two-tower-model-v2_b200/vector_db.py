@@ -55,6 +55,52 @@ def read_flat_ip_file(path: str) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------------------------
+# Native shard file: everything a rank needs to serve its block of catalog rows without
+# re-normalising or re-rounding - the fp32 rows faiss would store, their bf16 shadow (pitch Dp) and the error-bound
+# statistics - so an N-GPU server loads G files in parallel straight into device memory.
+#   magic "TTB2SHRD" | u32 version | u32 d | u32 dp | u64 rows | u64 id_offset | u64 n_total | f32 stats[4] |
+#   pad to 64 bytes | f32 xn[rows*d] | u16 xh[rows*dp]   (little endian)
+_SHARD_MAGIC = b"TTB2SHRD"
+_SHARD_HDR = struct.Struct("<8sIIIQQQ4f")
+_SHARD_HDR_BYTES = 64
+
+
+def write_native_shard(path: str, xn: np.ndarray, xh_bits: np.ndarray, stats: np.ndarray, id_offset: int = 0,
+                       n_total: Optional[int] = None) -> None:
+    """xn f32 [rows,d]; xh_bits u16 [rows,dp] (the bf16 bit patterns); stats f32 [4]."""
+    xn = np.ascontiguousarray(xn, dtype="<f4")
+    xh_bits = np.ascontiguousarray(xh_bits, dtype="<u2")
+    rows, d = xn.shape
+    if xh_bits.shape[0] != rows or xh_bits.shape[1] < d or xh_bits.shape[1] % 64 != 0:
+        raise ValueError(f"bf16 shadow shape {xh_bits.shape} does not match rows [{rows},{d}] (pitch must be a multiple of 64)")
+    st = np.asarray(stats, dtype="<f4").reshape(4)
+    hdr = _SHARD_HDR.pack(_SHARD_MAGIC, 1, d, xh_bits.shape[1], rows, int(id_offset),
+                          int(rows if n_total is None else n_total), *st.tolist())
+    with open(path, "wb") as f:
+        f.write(hdr.ljust(_SHARD_HDR_BYTES, b"\0"))
+        f.write(xn.tobytes())
+        f.write(xh_bits.tobytes())
+
+
+def read_native_shard(path: str):
+    """-> (xn f32 [rows,d], xh_bits u16 [rows,dp], stats f32 [4], id_offset, n_total); validates header and sizes."""
+    with open(path, "rb") as f:
+        hdr = f.read(_SHARD_HDR_BYTES)
+        if len(hdr) != _SHARD_HDR_BYTES:
+            raise ValueError(f"{path}: truncated shard header")
+        magic, version, d, dp, rows, id_offset, n_total, s0, s1, s2, s3 = _SHARD_HDR.unpack(hdr[:_SHARD_HDR.size])
+        if magic != _SHARD_MAGIC or version != 1:
+            raise ValueError(f"{path}: not a tt_b200 shard file (magic {magic!r}, version {version})")
+        if d <= 0 or dp < d or dp % 64 != 0 or n_total < rows:
+            raise ValueError(f"{path}: inconsistent shard header (d={d}, dp={dp}, rows={rows}, n_total={n_total})")
+        xn = np.fromfile(f, dtype="<f4", count=rows * d)
+        xh = np.fromfile(f, dtype="<u2", count=rows * dp)
+    if xn.size != rows * d or xh.size != rows * dp:
+        raise ValueError(f"{path}: truncated shard payload")
+    return xn.reshape(rows, d), xh.reshape(rows, dp), np.array([s0, s1, s2, s3], np.float32), int(id_offset), int(n_total)
+
+
+# ---------------------------------------------------------------------------------------------
 class _FlagRing:
     """A few pinned int32 slots: the status words of a search (uncertified count[, exchange time-out]) are
     copied into one of them asynchronously, so the host can look at them later without draining the stream."""
@@ -177,6 +223,24 @@ class FlatIPIndex:
         self.xh = torch.empty((xn.shape[0], self.dp), device=xn.device, dtype=torch.bfloat16)
         for s in range(0, xn.shape[0], chunk_rows):
             self._build_rows(s, min(chunk_rows, xn.shape[0] - s), normalize)
+        return self
+
+    def save_native(self, path: str, n_total: Optional[int] = None) -> None:
+        """Writes this index (one rank's shard) as a native shard file: no re-normalisation on load."""
+        write_native_shard(path, self.xn.cpu().numpy(), self.xh.view(torch.int16).cpu().numpy().view(np.uint16),
+                           self.stats.cpu().numpy(), self.id_offset, n_total)
+
+    @classmethod
+    def load_native(cls, path: str, device: Optional[torch.device] = None) -> "FlatIPIndex":
+        """Loads a native shard file straight into device memory (rows, bf16 shadow and statistics as stored)."""
+        xn, xh, stats, id_offset, _ = read_native_shard(path)
+        self = cls(xn.shape[1], device)
+        if xh.shape[1] != self.dp:
+            raise ValueError(f"{path}: bf16 pitch {xh.shape[1]} does not match this build's pitch {self.dp}")
+        self.xn = torch.from_numpy(xn).to(self.device)
+        self.xh = torch.from_numpy(xh.view(np.int16)).to(self.device).view(torch.bfloat16)
+        self.stats = torch.from_numpy(stats).to(self.device)
+        self.id_offset = id_offset
         return self
 
     def rows_host(self) -> np.ndarray:
