@@ -10,9 +10,9 @@ import torch
 ROOT = Path(__file__).resolve().parents[1]
 
 
-def _run(*args):
+def _run(*args, env=None):
     return subprocess.run([sys.executable, str(ROOT / "bench.py"), *args], capture_output=True, text=True, cwd=ROOT,
-                          timeout=600)
+                          timeout=600, env=env)
 
 
 def test_reference_arm_json_line():
@@ -24,6 +24,8 @@ def test_reference_arm_json_line():
     assert line["config"]["workload"] == "flat_ip_top10_20000x384_nq16"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"]
+    assert line["metric"] == "exact top-10 queries/s, 20000x384 catalog"
+    assert line["extrapolated"]["is_extrapolated"] is False and line["extrapolated"]["sample_rows"] == 20000
     assert line["e2e"] == {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["vs_baseline"] is None and line["gpu_launches"] == 0
 
@@ -33,3 +35,51 @@ def test_product_arm_needs_cuda():
         return
     r = _run("--steps", "1", "--catalog-rows", "20000", "--nq", "16")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_under_torchrun_uses_all_threads_and_is_bounded():
+    """The driver launches the reference arm like the product arm (torchrun for N > 1), and torchrun exports
+    OMP_NUM_THREADS=1: rank 0 must still use every host core, sample the catalog to its time budget, say that the
+    number is extrapolated, and the other ranks must exit 0 without printing a line."""
+    import os
+    import socket
+    import time
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    env = dict(os.environ, TT_BENCH_REF_BUDGET_S="4")
+    env.pop("OMP_NUM_THREADS", None)
+    t = time.time()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(ROOT / "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, "only rank 0 prints"
+    line = lines[0]
+    ncpu = len(os.sched_getaffinity(0))
+    assert line["cpu_baseline"]["cores"] == ncpu, "torchrun's OMP_NUM_THREADS=1 must not throttle the CPU arm"
+    assert line["n_gpus"] == 2 and line["config"]["workload"] == "flat_ip_top100_10000000x384_nq4096"
+    assert line["metric"] == "exact top-100 queries/s, 10Mx384 catalog"
+    ex = line["extrapolated"]
+    assert ex["is_extrapolated"] and "extrapolated" in line["dtype"] and "EXTRAPOLATED" in line["cpu_baseline"]["sample"]
+    assert abs(line["ms_per_step"] - ex["measured_ms_per_sample_step"] * ex["scale"]) < 1e-6 * line["ms_per_step"]
+    assert time.time() - t < 120
+
+
+def test_parity_comparator_tie_rules():
+    """bench.compare_topk_device: score errors, swaps inside / outside ties and boundary ties."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    rs = torch.tensor([[0.9, 0.8, 0.7, 0.6]])
+    ri = torch.tensor([[10, 11, 12, 13]])
+    assert bench.compare_topk_device(rs.clone(), ri.clone(), rs, ri)["ok"]
+    assert not bench.compare_topk_device(rs + 2e-5, ri, rs, ri)["ok"]                       # score tolerance
+    sw = torch.tensor([[10, 12, 11, 13]])
+    assert not bench.compare_topk_device(rs, sw, rs, ri)["ok"]                              # swap across a 0.1 gap
+    rt = torch.tensor([[0.9, 0.8, 0.8 - 5e-7, 0.6]])
+    assert bench.compare_topk_device(rt, sw, rt, ri)["ok"]                                  # swap inside a tie
+    other = torch.tensor([[10, 11, 12, 99]])
+    assert bench.compare_topk_device(rs, other, rs, ri)["ok"]                               # boundary tie (same score)
+    assert not bench.compare_topk_device(rs - torch.tensor([[0, 0, 0, 5e-6]]), other, rs, ri)["ok"]

@@ -378,3 +378,84 @@ def test_native_shard_save_load_search_identical(tmp_path):
     s1, i1, _ = idx.search_checked_device(q, 10)
     s2, i2, _ = back.search_checked_device(q, 10)
     assert torch.equal(s1, s2) and torch.equal(i1, i2) and int(i1.min()) >= 777
+
+
+def test_wide_rows_route_to_exact_path():
+    """D > 1024 does not fit the resident-query scan: tt_flat_search serves it through the fp32 exact path
+    (faiss has no such limit, vector_db.py:160)."""
+    rng = np.random.default_rng(51)
+    x = rng.standard_normal((3000, 1536)).astype(np.float32)
+    q = rng.standard_normal((5, 1536)).astype(np.float32)
+    check(build(x), x, q, 10)
+
+
+def test_float64_catalog_is_normalised_in_float64_like_the_reference():
+    """vector_db.py:44-45,51 normalises in the input dtype and then casts to f32."""
+    import two_tower_model_v2_b200 as pkg
+    rng = np.random.default_rng(52)
+    x = rng.standard_normal((5000, 64)) * 3.0
+    db = pkg.VectorDatabase(64)
+    db.build_index(x, [str(i) for i in range(5000)])
+    ref = (x / (np.linalg.norm(x, axis=1, keepdims=True) + 1e-8)).astype(np.float32)
+    assert np.array_equal(db.index.xn.cpu().numpy(), ref)
+
+
+def test_appending_rows_keeps_earlier_rows_and_results():
+    """FlatIPIndex.add grows its storage geometrically; rows already stored and their order are kept."""
+    rng = np.random.default_rng(53)
+    x = rng.standard_normal((9000, 96)).astype(np.float32)
+    q = rng.standard_normal((7, 96)).astype(np.float32)
+    import two_tower_model_v2_b200 as pkg
+    idx = pkg.FlatIPIndex(96)
+    for lo in range(0, 9000, 1000):
+        idx.add(x[lo:lo + 1000])
+    assert idx.ntotal == 9000 and idx._xn_store.shape[0] >= 9000
+    check(idx, x, q, 10)
+
+
+def test_async_search_from_worker_thread_and_micro_batcher():
+    """The completion events of search_async / search_host_async are recorded on the INDEX's stream, whatever the
+    calling thread's current device is: a MicroBatcher worker thread (fresh thread, default device) must get
+    complete, certified results."""
+    import threading
+    import two_tower_model_v2_b200 as pkg
+    rng = np.random.default_rng(54)
+    x = rng.standard_normal((50000, 64)).astype(np.float32)
+    q = rng.standard_normal((40, 64)).astype(np.float32)
+    idx = build(x)
+    xn, qn = fo.normalize_rows(x), fo.normalize_rows(q)
+    rs, ri = fo.search(xn, qn, 10)
+
+    def batch_fn(payloads, k):
+        s, i, _ = idx.search_host_async(np.stack(payloads), k).result()
+        return pkg.ArrayRows(i, s)
+    out = [None] * 40
+    with pkg.MicroBatcher(batch_fn, max_batch=16, max_wait_ms=1.0) as mb:
+        def client(c):
+            for j in range(c, 40, 8):
+                out[j] = mb(q[j], 10)
+        ths = [threading.Thread(target=client, args=(c,)) for c in range(8)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+    ids = np.stack([o.ids for o in out])
+    sc = np.stack([o.scores for o in out])
+    ok, msg = fo.compare_topk(sc, ids, rs, ri, xn, qn)
+    assert ok, msg
+
+
+def test_index_on_non_current_device():
+    """FlatIPIndex(d, device=cuda:1) used while cuda:0 is current: events / copies follow the index."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import two_tower_model_v2_b200 as pkg
+    rng = np.random.default_rng(55)
+    x = rng.standard_normal((30000, 64)).astype(np.float32)
+    q = rng.standard_normal((9, 64)).astype(np.float32)
+    torch.cuda.set_device(0)
+    idx = pkg.FlatIPIndex(64, device=torch.device("cuda:1"))
+    idx.add(x)
+    s, i = idx.search(q, 10)
+    xn, qn = fo.normalize_rows(x), fo.normalize_rows(q)
+    rs, ri = fo.search(xn, qn, 10)
+    ok, msg = fo.compare_topk(s, i, rs, ri, xn, qn)
+    assert ok, msg

@@ -10,7 +10,7 @@ CUDA kernels behind the C-ABI in include/tt_b200.h:
 The directory is named `two-tower-model-v2_b200`; import it as `two_tower_model_v2_b200`
 (the root-level `two_tower_model_v2_b200.py` aliases it).
 """
-from .batcher import MicroBatcher
+from .batcher import ArrayRows, MicroBatcher
 from .buyer_tower import BuyerTower
 from .config import get_event_weight
 from .retrieval import RetrievalPipeline
@@ -18,5 +18,5 @@ from .sharded import ShardedFlatIPIndex, shard_bounds
 from .vector_db import (FlatIPIndex, VectorDatabase, read_flat_ip_file, read_native_shard, write_flat_ip_file,
                         write_native_shard)
 
-__all__ = ["BuyerTower", "VectorDatabase", "FlatIPIndex", "ShardedFlatIPIndex", "RetrievalPipeline", "MicroBatcher", "shard_bounds",
+__all__ = ["BuyerTower", "VectorDatabase", "FlatIPIndex", "ShardedFlatIPIndex", "RetrievalPipeline", "MicroBatcher", "ArrayRows", "shard_bounds",
            "get_event_weight", "read_flat_ip_file", "write_flat_ip_file", "read_native_shard", "write_native_shard"]

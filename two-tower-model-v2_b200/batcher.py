@@ -20,6 +20,24 @@ from concurrent.futures import Future
 from typing import Any, Callable, List, Optional, Sequence, Tuple
 
 
+class ArrayRows:
+    """Batched results as two arrays (ids i64 [B,k], scores f32 [B,k]) that MicroBatcher can hand out per request
+    without building Python lists: `rows[r][:k]` is a view pair `(ids[r,:k], scores[r,:k])` (`.ids`, `.scores`)."""
+    __slots__ = ("ids", "scores")
+
+    def __init__(self, ids, scores):
+        self.ids, self.scores = ids, scores
+
+    def __len__(self):
+        return len(self.ids)
+
+    def __getitem__(self, r):
+        return ArrayRows(self.ids[r], self.scores[r])
+
+    def __iter__(self):
+        return iter((self.ids, self.scores))
+
+
 class MicroBatcher:
     def __init__(self, batch_fn: Callable[[List[Any], int], Sequence[Any]], max_batch: int = 128,
                  max_wait_ms: float = 0.2):

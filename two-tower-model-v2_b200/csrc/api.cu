@@ -77,7 +77,7 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
 extern "C" __attribute__((visibility("default"))) size_t tt_flat_search_workspace_bytes(int64_t N, int D, int nq, int K) {
   if (N < 1 || D < 1 || nq < 1 || K < 1) return 0;
   const ScanPlan pl = make_scan_plan(N, D, nq, K);
-  if (pl.route_exact) return tt_flat_search_exact_workspace_bytes(N, D, nq, K);
+  if (pl.route_exact || !pl.supported) return tt_flat_search_exact_workspace_bytes(N, D, nq, K);
   return search_ws_layout(pl, D, nq).total;
 }
 
@@ -96,14 +96,11 @@ static int flat_search_impl(const float* q, int nq, const float* Xn, const void*
   if (nq == 0) return TT_OK;
 
   const ScanPlan pl = make_scan_plan(N, D, nq, K);
-  if (!pl.supported) {
-    set_error("tt_flat_search: embedding dimension too large for the resident-query scan (D <= 1024 supported)");
-    return TT_ERR_UNSUPPORTED;
-  }
   TT_CHECK_ARG(workspace != nullptr, "null workspace");
   TT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
-  if (pl.route_exact) {
-    // K is too large a fraction of N for a sampled threshold: the fp32 exact path serves the batch.
+  if (pl.route_exact || !pl.supported) {
+    // K is too large a fraction of N for a sampled threshold, or the rows are too wide for the resident-query
+    // scan (D > 1024): the fp32 exact path serves the batch.
     fill_int_kernel<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, 1);
     TT_CHECK_LAUNCH();
     if (bound) {   // the exact path scores every row: nothing is left unbounded

@@ -50,11 +50,17 @@ p2p_push_kernel(const uint4* __restrict__ src, size_t n16, PushPeers peers, int 
 
 // One warp: lane g waits until rank g's record of exchange `seq` has landed.  A rank that never shows up
 // must not hang the device: after `timeout_cycles` the kernel gives up and reports through *timed_out.
-__global__ void p2p_wait_kernel(const int* __restrict__ flags, int G, int seq, long long timeout_cycles, int* timed_out) {
-  const long long t0 = clock64();
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void p2p_wait_kernel(const int* __restrict__ flags, int G, int seq, unsigned long long timeout_ns, int* timed_out) {
+  const unsigned long long t0 = globaltimer_ns();     // wall-clock nanoseconds: independent of the SM clock
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     while (ld_acquire_sys(flags + g) - seq < 0) {
-      if (clock64() - t0 > timeout_cycles) { atomicExch(timed_out, seq); return; }
+      if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(timed_out, seq); return; }
       __nanosleep(200);
     }
   }
@@ -90,10 +96,9 @@ extern "C" __attribute__((visibility("default"))) int tt_p2p_wait(const int32_t*
                                                      void* stream) {
   TT_CHECK_ARG(flags && timed_out, "null pointer");
   TT_CHECK_ARG(G >= 1 && G <= P2P_MAX_RANKS, "need 1 <= G <= 64");
-  // clock64() ticks at the SM clock (<= ~2 GHz on B200); a fixed 2 GHz keeps the bound within a small factor
-  // without querying the device (cudaDevAttrClockRate costs milliseconds per call on this driver).
-  const long long cycles = (long long)(timeout_seconds * 2.0e9);
-  p2p_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(flags, G, seq, cycles, timed_out);
+  TT_CHECK_ARG(timeout_seconds > 0.0 && timeout_seconds < 3600.0, "timeout_seconds out of range");
+  const unsigned long long ns = (unsigned long long)(timeout_seconds * 1.0e9);
+  p2p_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(flags, G, seq, ns, timed_out);
   TT_CHECK_LAUNCH();
   return TT_OK;
 }

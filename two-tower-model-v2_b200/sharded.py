@@ -114,27 +114,60 @@ class P2PExchange:
         import ctypes
         self._ctypes = ctypes
         self.total_bytes = off
-        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-        with torch.cuda.device(device):
-            self.check(self.lib.tt_p2p_alloc(off, ctypes.byref(ptr), handle), "tt_p2p_alloc")
-        self.base = int(ptr.value)
+        self.base, self.peer_base, self.buf = None, [], None
+
+        def agree(ok: bool) -> bool:
+            """Every rank leaves each set-up stage together: MIN over the ranks' success flags."""
+            t = torch.tensor([1 if ok else 0], device=device, dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(int(t.item()))
+
+        # stage 1: allocate the receive buffer
+        ptr, handle, err = ctypes.c_void_p(), ctypes.create_string_buffer(64), None
+        try:
+            with torch.cuda.device(device):
+                self.check(self.lib.tt_p2p_alloc(off, ctypes.byref(ptr), handle), "tt_p2p_alloc")
+            self.base = int(ptr.value)
+        except Exception as e:
+            err = e
+        if not agree(err is None):
+            self._abort()
+            raise RuntimeError(f"P2PExchange: receive-buffer allocation failed on some rank ({err!r} here)")
+        # stage 2: exchange the IPC handles and map every peer
         handles = [None] * G
         dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        self.peer_base = []
-        for r in range(G):
-            if r == self.rank:
-                self.peer_base.append(self.base)
-                continue
-            p = ctypes.c_void_p()
-            with torch.cuda.device(device):
-                self.check(self.lib.tt_p2p_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(p)), "tt_p2p_open")
-            self.peer_base.append(int(p.value))
+        self.peer_base = [None] * G
+        try:
+            for r in range(G):
+                if r == self.rank:
+                    self.peer_base[r] = self.base
+                    continue
+                p = ctypes.c_void_p()
+                with torch.cuda.device(device):
+                    self.check(self.lib.tt_p2p_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(p)), "tt_p2p_open")
+                self.peer_base[r] = int(p.value)
+        except Exception as e:
+            err = e
+        if not agree(err is None):
+            dist.barrier(group=group)       # nobody frees a buffer a peer may still be mapping
+            self._abort()
+            raise RuntimeError(f"P2PExchange: mapping a peer's buffer failed on some rank ({err!r} here)")
         # zero-copy torch view of the local buffer (kernels downstream take torch tensors)
         self.buf = torch.as_tensor(_RawCudaBuffer(self.base, off), device=device)
         self.done = torch.zeros(len(self.nbytes), dtype=torch.int32, device=device)
         self.seq = [0] * len(self.nbytes)
         self._ptr_arrays = {}
         dist.barrier(group=group)       # every rank has mapped every buffer before the first push
+
+    def _abort(self) -> None:
+        """Local clean-up of a failed set-up: unmap whatever peers were opened, free the own buffer."""
+        with torch.cuda.device(self.device):
+            for r, p in enumerate(self.peer_base):
+                if p is not None and r != self.rank:
+                    self.lib.tt_p2p_close(self._ctypes.c_void_p(p))
+            if self.base is not None:
+                self.lib.tt_p2p_free(self._ctypes.c_void_p(self.base))
+        self.base, self.peer_base, self.buf = None, [], None
 
     def close(self) -> None:
         """Collective: every rank calls it after its last exchange.  Order matters for CUDA IPC: all ranks finish
@@ -192,8 +225,13 @@ class ShardedFlatIPIndex:
     `merge(gathered[G,nbytes] uint8, layout, nq, k) -> (scores, ids, flags, n_uncertified)`.
     """
 
+    MAX_P2P_SHAPES = 4
+
     def __init__(self, local_index, n_total: int, group=None, merge: Optional[Callable] = None, exchange: str = "auto"):
+        if n_total >= 1 << 32:
+            raise ValueError("sharded catalogs are limited to 2^32 - 1 rows (merge keys carry 32-bit ids)")
         self.local = local_index
+        self._n_local_min = None
         self.n_total = int(n_total)
         self.group = group
         self._merge = merge if merge is not None else _merge_cuda
@@ -240,8 +278,17 @@ class ShardedFlatIPIndex:
             self.exchange_used = self.exchange_used or "nccl"
             return None
         key = (nq, k, world)
+        if key in self._p2p:
+            self._p2p[key] = self._p2p.pop(key)       # most recently used last
         if key not in self._p2p:
             from ._native import TT_SHARD_TOPR
+            # Bounded: a server with many batch shapes must not keep one IPC buffer set per shape for ever.  Every
+            # rank sees the same sequence of shapes, so evicting the least recently used one is collective-safe.
+            while len(self._p2p) >= self.MAX_P2P_SHAPES:
+                old_key = next(iter(self._p2p))
+                old = self._p2p.pop(old_key)
+                if old is not None:
+                    old.close()
             ok, ex = 1, None
             try:
                 ex = P2PExchange([nq * TT_SHARD_TOPR * 4, lay.nbytes], device, self.group)
@@ -256,6 +303,24 @@ class ShardedFlatIPIndex:
             self.exchange_used = "p2p" if self._p2p[key] is not None else "nccl"
         return self._p2p[key]
 
+    def _validate(self, world: int, device) -> None:
+        """Once, collectively: the shards must add up to n_total, and every rank learns the smallest shard so that
+        all ranks take the same branch (global threshold vs per-shard) whatever partition the caller loaded."""
+        if self._n_local_min is not None:
+            return
+        n_local = int(self.local.ntotal)
+        if world > 1:
+            t = torch.tensor([n_local, -n_local], device=device, dtype=torch.int64)
+            tot = torch.tensor([n_local], device=device, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+            n_min, n_max, total = int(t[0]), -int(t[1]), int(tot[0])
+        else:
+            n_min = n_max = total = n_local
+        if total != self.n_total:
+            raise ValueError(f"shards hold {total} rows in total but n_total = {self.n_total}")
+        self._n_local_min, self._n_local_max = n_min, n_max
+
     def _local_search(self, q: torch.Tensor, k: int, k_local: int, world: int, views, p2p=None, status=None) -> None:
         """Fills this rank's record.  With every shard holding >= k rows and a plan for it, all ranks use ONE
         threshold estimated from a sample of the whole catalog (a small all-gather of per-rank top-r sampled
@@ -263,9 +328,9 @@ class ShardedFlatIPIndex:
         own threshold."""
         scores, ids, bound, flags = views
         nq = q.shape[0]
-        n_local_min = self.n_total - (world - 1) * (-(-self.n_total // world))     # the last shard is the smallest
+        n_local_min = self._n_local_min if self._n_local_min is not None else self.local.ntotal
         plan_ok = getattr(self.local, "shard_plan_ok", None)
-        if world > 1 and k_local == k and plan_ok is not None and plan_ok(self.n_total, nq, k, max(n_local_min, 0)):
+        if world > 1 and n_local_min >= k and plan_ok is not None and plan_ok(self.n_total, nq, k, max(n_local_min, 0)):
             from ._native import TT_SHARD_TOPR
             key = ("topr", nq, world)
             bufs = self._bufs.get(key)
@@ -288,6 +353,7 @@ class ShardedFlatIPIndex:
         from .vector_db import PendingSearch
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         nq = q.shape[0]
+        self._validate(world, q.device)
         lay, rec, gathered = self._buffers(nq, k, q.device, world)
         views = record_views(rec, lay, nq, k)
         scores, ids, bound, flags = views
@@ -322,25 +388,34 @@ class ShardedFlatIPIndex:
             # Re-run the flagged queries alone (this rank's record buffer may already hold a later batch):
             # exact fp32 search of every shard, a small exchange, merge, scatter into the result.
             rows = torch.nonzero(fl != 1).flatten()
-            nsel = int(rows.numel())
-            lay2 = record_layout(nsel, k)
-            rec2 = torch.zeros(lay2.nbytes, dtype=torch.uint8, device=q.device)
-            gathered2 = torch.zeros((world, lay2.nbytes), dtype=torch.uint8, device=q.device)
-            s_l, i_l, b_l, f_l = record_views(rec2, lay2, nsel, k)
-            s_l.fill_(float("-inf"))
-            i_l.fill_(-1)
-            b_l.fill_(float("-inf"))
-            f_l.fill_(1)
-            self.local.search_exact_into(q[rows].contiguous(), k_local, s_l, i_l,
-                                         torch.arange(nsel, device=q.device, dtype=torch.int32))
-            self._exchange(rec2, gathered2, world)
-            s2, i2, fl2, n_unc2 = self._merge(gathered2, lay2, nsel, k)
-            if int(n_unc2):
-                raise RuntimeError("sharded search: queries still uncertified after the exact re-run")
+            s2, i2 = self.search_exact_device(q[rows].contiguous(), k)
             s[rows] = s2
             i[rows] = i2
             return s, i, n_bad
         return PendingSearch(finish)
+
+    def search_exact_device(self, q: torch.Tensor, k: int):
+        """Always-exact fp32 path over the sharded catalog (collective: every rank calls it with the same q):
+        fp32 exact search of every shard, one exchange of the records (NCCL / plain copy), merge.  Serves the
+        queries the global certificate rejects and the parity checks of bench.py / tests."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        nsel = q.shape[0]
+        k_local = min(k, self.local.ntotal)
+        lay2 = record_layout(nsel, k)
+        rec2 = torch.zeros(lay2.nbytes, dtype=torch.uint8, device=q.device)
+        gathered2 = torch.zeros((world, lay2.nbytes), dtype=torch.uint8, device=q.device)
+        s_l, i_l, b_l, f_l = record_views(rec2, lay2, nsel, k)
+        s_l.fill_(float("-inf"))
+        i_l.fill_(-1)
+        b_l.fill_(float("-inf"))
+        f_l.fill_(1)
+        if k_local > 0:
+            self.local.search_exact_into(q, k_local, s_l, i_l, torch.arange(nsel, device=q.device, dtype=torch.int32))
+        self._exchange(rec2, gathered2, world)
+        s2, i2, fl2, n_unc2 = self._merge(gathered2, lay2, nsel, k)
+        if int(n_unc2):
+            raise RuntimeError("sharded search: queries still uncertified after the exact re-run")
+        return s2, i2
 
     def search_device(self, q: torch.Tensor, k: int):
         """q replicated on every rank -> global (scores, ids) [nq,k] on every rank, and the number of
@@ -376,23 +451,33 @@ class ShardedFlatIPIndex:
                 (torch.empty((nl, d), dtype=torch.float32, pin_memory=True),
                  torch.empty((nl, k), dtype=torch.float32, pin_memory=True),
                  torch.empty((nl, k), dtype=torch.int64, pin_memory=True)) for _ in range(3)]}
-        hq, hs, hi = ring["sets"][ring["next"]]
-        ring["next"] = (ring["next"] + 1) % 3
+        slot = ring["next"]
+        hq, hs, hi = ring["sets"][slot]
+        ring["next"] = (slot + 1) % 3
+        evs = ring.setdefault("h2d_done", [None] * 3)
+        if evs[slot] is not None:
+            evs[slot].synchronize()      # the previous user's H2D copy of this staging set has been consumed
         hq.copy_(torch.from_numpy(q_local))
-        dq_local = hq.to(dev, non_blocking=True)
-        dq_all = torch.empty((world, nl, d), device=dev, dtype=torch.float32)    # fresh: the exact re-run may need it later
-        if world > 1:
-            dist.all_gather_into_tensor(dq_all.view(-1), dq_local.view(-1), group=self.group)
-        else:
-            dq_all[0].copy_(dq_local)
-        pending = self.search_async(dq_all.view(world * nl, d), k)
+        stream = torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            dq_local = hq.to(dev, non_blocking=True)
+            evs[slot] = torch.cuda.Event()
+            evs[slot].record(stream)
+            dq_all = torch.empty((world, nl, d), device=dev, dtype=torch.float32)    # fresh: the exact re-run may need it later
+            if world > 1:
+                dist.all_gather_into_tensor(dq_all.view(-1), dq_local.view(-1), group=self.group)
+            else:
+                dq_all[0].copy_(dq_local)
+            pending = self.search_async(dq_all.view(world * nl, d), k)
 
         def finish():
             scores, ids, n_bad = pending.result()
-            hs.copy_(scores[rank * nl:(rank + 1) * nl], non_blocking=True)
-            hi.copy_(ids[rank * nl:(rank + 1) * nl], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
+            st = torch.cuda.current_stream(dev)
+            with torch.cuda.device(dev):
+                hs.copy_(scores[rank * nl:(rank + 1) * nl], non_blocking=True)
+                hi.copy_(ids[rank * nl:(rank + 1) * nl], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
             ev.synchronize()
             return hs.numpy().copy(), hi.numpy().copy(), n_bad
         return PendingSearch(finish)

@@ -103,24 +103,33 @@ def read_native_shard(path: str):
 # ---------------------------------------------------------------------------------------------
 class _FlagRing:
     """A few pinned int32 slots: the status words of a search (uncertified count[, exchange time-out]) are
-    copied into one of them asynchronously, so the host can look at them later without draining the stream."""
+    copied into one of them asynchronously, so the host can look at them later without draining the stream.
+    The completion event is recorded on the stream of the STATUS TENSOR's device (the index's device), not on
+    the calling thread's current device: a worker thread that never called set_device still waits for the right
+    stream.  A slot recycled before it was read (more than `n` searches in flight) is detected and raised."""
     WIDTH = 2
 
-    def __init__(self, n: int = 64):     # more searches than this in flight would recycle a slot
+    def __init__(self, n: int = 64):
         self.host = torch.zeros((n, self.WIDTH), dtype=torch.int32, pin_memory=True)
         self.n, self.next = n, 0
+        self.gen = [0] * n
 
     def post(self, status_dev: torch.Tensor):
         slot = self.next
         self.next = (self.next + 1) % self.n
+        self.gen[slot] += 1
         w = int(status_dev.numel())
-        self.host[slot, :w].copy_(status_dev, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        return slot, ev, w
+        stream = torch.cuda.current_stream(status_dev.device)
+        with torch.cuda.stream(stream):
+            self.host[slot, :w].copy_(status_dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return slot, ev, w, self.gen[slot]
 
-    def read(self, slot: int, ev, w: int = 1):
+    def read(self, slot: int, ev, w: int = 1, gen: int = None):
         ev.synchronize()
+        if gen is not None and self.gen[slot] != gen:
+            raise RuntimeError(f"tt_b200: more than {self.n} searches in flight: the status slot of this search was recycled")
         vals = self.host[slot, :w].tolist()
         return vals[0] if w == 1 else vals
 
@@ -156,6 +165,8 @@ class FlatIPIndex:
         self.dp = int(_native.load().tt_flat_pitch(self.d))
         self.xn: Optional[torch.Tensor] = None
         self.xh: Optional[torch.Tensor] = None
+        self._xn_store: Optional[torch.Tensor] = None     # capacity >= ntotal rows; xn / xh are its leading views
+        self._xh_store: Optional[torch.Tensor] = None
         self.stats = torch.zeros(4, device=self.device, dtype=torch.float32)
         self.id_offset = 0
         self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
@@ -169,13 +180,20 @@ class FlatIPIndex:
 
     # -- build -----------------------------------------------------------------------------
     def _alloc(self, n: int) -> None:
-        xn = torch.empty((n, self.d), device=self.device, dtype=torch.float32)
-        xh = torch.empty((n, self.dp), device=self.device, dtype=torch.bfloat16)
+        """Makes room for n rows.  The first build allocates exactly n rows (a 10M-row catalog must not be over-
+        allocated); later `add` calls grow the storage geometrically (x1.5), so appending m batches copies
+        O(total) rows instead of O(m * total)."""
         old = self.ntotal
-        if old:
-            xn[:old].copy_(self.xn)
-            xh[:old].copy_(self.xh)
-        self.xn, self.xh = xn, xh
+        cap = 0 if self._xn_store is None else int(self._xn_store.shape[0])
+        if n > cap:
+            new_cap = n if old == 0 else max(n, cap + cap // 2)
+            xn = torch.empty((new_cap, self.d), device=self.device, dtype=torch.float32)
+            xh = torch.empty((new_cap, self.dp), device=self.device, dtype=torch.bfloat16)
+            if old:
+                xn[:old].copy_(self.xn)
+                xh[:old].copy_(self.xh)
+            self._xn_store, self._xh_store = xn, xh
+        self.xn, self.xh = self._xn_store[:n], self._xh_store[:n]
         self._ws.clear()
         self._exact_ws = None
 
@@ -219,8 +237,8 @@ class FlatIPIndex:
         if not (xn.is_cuda and xn.dtype == torch.float32 and xn.dim() == 2 and xn.is_contiguous()):
             raise ValueError("adopt() needs a contiguous CUDA float32 [N,D] tensor")
         self = cls(xn.shape[1], xn.device)
-        self.xn = xn
-        self.xh = torch.empty((xn.shape[0], self.dp), device=xn.device, dtype=torch.bfloat16)
+        self.xn = self._xn_store = xn
+        self.xh = self._xh_store = torch.empty((xn.shape[0], self.dp), device=xn.device, dtype=torch.bfloat16)
         for s in range(0, xn.shape[0], chunk_rows):
             self._build_rows(s, min(chunk_rows, xn.shape[0] - s), normalize)
         return self
@@ -237,8 +255,8 @@ class FlatIPIndex:
         self = cls(xn.shape[1], device)
         if xh.shape[1] != self.dp:
             raise ValueError(f"{path}: bf16 pitch {xh.shape[1]} does not match this build's pitch {self.dp}")
-        self.xn = torch.from_numpy(xn).to(self.device)
-        self.xh = torch.from_numpy(xh.view(np.int16)).to(self.device).view(torch.bfloat16)
+        self.xn = self._xn_store = torch.from_numpy(xn).to(self.device)
+        self.xh = self._xh_store = torch.from_numpy(xh.view(np.int16)).to(self.device).view(torch.bfloat16)
         self.stats = torch.from_numpy(stats).to(self.device)
         self.id_offset = id_offset
         return self
@@ -263,7 +281,8 @@ class FlatIPIndex:
         """Asynchronous search of CUDA f32 queries [nq,D] on the current stream.
 
         Returns (scores [nq,k] f32, ids [nq,k] i64, flags [nq] i32, n_uncertified [1] i32) device
-        tensors; rows with flags == 0 (see include/tt_b200.h) must be passed to `search_exact_device`.
+        tensors; rows with flags != 1 (1 = certified exact, <= 0 = -(reason bits), see include/tt_b200.h) must be
+        passed to `search_exact_device` (`search_checked_device` / `search_async` do both).
         """
         if self.ntotal == 0:
             raise ValueError("empty index")
@@ -446,18 +465,28 @@ def host_search_async(owner, search_async, device, d: int, q: np.ndarray, k: int
             (torch.empty((nq, d), dtype=torch.float32, pin_memory=True),
              torch.empty((nq, k), dtype=torch.float32, pin_memory=True),
              torch.empty((nq, k), dtype=torch.int64, pin_memory=True)) for _ in range(depth)]}
-    hq, hs, hi = ring["sets"][ring["next"]]
-    ring["next"] = (ring["next"] + 1) % depth
+    slot = ring["next"]
+    hq, hs, hi = ring["sets"][slot]
+    ring["next"] = (slot + 1) % depth
+    evs = ring.setdefault("h2d_done", [None] * depth)
+    if evs[slot] is not None:
+        evs[slot].synchronize()          # the previous user's H2D copy of this staging set has been consumed
     hq.copy_(torch.from_numpy(q))
-    dq = hq.to(device, non_blocking=True)
-    pending = search_async(dq, k)
+    stream = torch.cuda.current_stream(device)
+    with torch.cuda.device(device):
+        dq = hq.to(device, non_blocking=True)
+        evs[slot] = torch.cuda.Event()
+        evs[slot].record(stream)
+        pending = search_async(dq, k)
 
     def finish():
         scores, ids, n_bad = pending.result()        # exact re-run (if any) is enqueued before the copies below
-        hs.copy_(scores, non_blocking=True)
-        hi.copy_(ids, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
+        st = torch.cuda.current_stream(device)
+        with torch.cuda.device(device):
+            hs.copy_(scores, non_blocking=True)
+            hi.copy_(ids, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
         ev.synchronize()
         return hs.numpy().copy(), hi.numpy().copy(), n_bad
     return PendingSearch(finish)
@@ -480,7 +509,13 @@ class VectorDatabase:
         if dim != self.embedding_dim:
             raise ValueError(f"Embedding dimension mismatch: expected {self.embedding_dim}, got {dim}")
         index = FlatIPIndex(self.embedding_dim)
-        index.add(np.asarray(embeddings), normalize=True)
+        embeddings = np.asarray(embeddings)
+        if embeddings.dtype == np.float64:
+            # the reference normalises in the INPUT dtype and only then casts to f32 (vector_db.py:44-45,51)
+            norms = np.linalg.norm(embeddings, axis=1, keepdims=True)
+            index.add((embeddings / (norms + 1e-8)).astype(np.float32), normalize=False)
+        else:
+            index.add(embeddings, normalize=True)
         self.index = index
         self.product_ids = product_ids
         self.id_to_index = {pid: idx for idx, pid in enumerate(product_ids)}
