@@ -12,7 +12,7 @@
  * arithmetic it replaces:
  *
  *   src/models/buyer_tower.py:43-68    weighted_average        -> tt_pool_weighted[_gather]
- *   src/models/buyer_tower.py:70-101   attention_aggregation   -> tt_attention_logits + tt_pool_attention[_gather]
+ *   src/models/buyer_tower.py:70-101   attention_aggregation   -> tt_pool_attention_fused (dense), tt_attention_logits + tt_pool_attention[_gather]
  *   src/inference/vector_db.py:44-54   build_index (normalise + IndexFlatIP.add) -> tt_flat_build
  *   src/inference/vector_db.py:152-160 retrieve  (renormalise + IndexFlatIP.search) -> tt_flat_search
  *   src/inference/vector_db.py:189-197 retrieve_batch (same, nq > 1)            -> tt_flat_search
@@ -90,6 +90,35 @@ int tt_pool_attention(const float* x, const float* logits, const float* w, float
 int tt_pool_attention_gather(const float* table, int64_t N, const float* row_logits,
                              float zero_row_logit, const int64_t* idx, const float* w,
                              float* out, int B, int S, int D, void* stream);
+
+/* Pooling out of a row-SHARDED item table (BASELINE config C5: the catalog, which is the item table of the
+ * /retrieve path - src/inference/encoder.py:276-303 pools the item embeddings of the history - is split over the
+ * GPUs).  Owner computes: idx holds GLOBAL row ids; this rank reduces the positions whose row it owns
+ * ([row_lo, row_lo + N_local), read from `table` = its local rows) into partial f32 [B, D+4] = {acc[D], m, l, 0, 0}
+ * (D % 4 == 0: every record row stays 16-byte aligned):
+ *   weighted_avg (row_logits == NULL): acc = sum w_s x_s, l = sum w_s, m = 0
+ *   attention (row_logits f32 [N_local]): c_s = logit_s * w_s, m = max c_s, l = sum e^(c_s-m), acc = sum e^(c_s-m) x_s
+ * A position with idx outside [0, N_total) is an all-zero row: nothing for acc, but its weight / softmax mass
+ * (logit = zero_row_logit) is kept by the rank called with owns_invalid = 1 (exactly one rank).
+ * tt_pool_partial_merge: the all-gathered partials f32 [G, B, D+4] -> out f32 [B, D], L2-normalised; same result as
+ * tt_pool_*_gather on an unsharded table up to fp32 summation order. */
+int tt_pool_partial_gather(const float* table, int64_t N_local, int64_t row_lo, int64_t N_total, int owns_invalid,
+                           const float* row_logits, float zero_row_logit, const int64_t* idx, const float* w,
+                           float* partial, int B, int S, int D, void* stream);
+int tt_pool_partial_merge(const float* partials_g, int G, int attention, float* out, int B, int D, void* stream);
+
+/* attention_aggregation in ONE kernel and one pass over x in HBM (buyer_tower.py:70-101): the score MLP runs on
+ * the tensor cores (fp16 two-piece split of both operands, fp32 accumulation in TMEM: fp32-accurate) while the rows
+ * stream in through TMA, and the softmax-weighted row sum + L2 normalisation re-read the rows while they are still in
+ * L2.  Fused for D % 64 == 0, D <= 384, H <= 128, S <= 8192, B*S >= 4096; any other shape runs tt_attention_logits +
+ * tt_pool_attention behind the same entry point.  Inputs outside the fp16 range after scaling (|x| > 4094, inf, nan)
+ * are detected on the device and recomputed by a predicated fp32 CUDA-core kernel (no host synchronisation).
+ * workspace: tt_pool_attention_fused_workspace_bytes(B,S,D,H) bytes of device memory, 256-byte aligned. */
+size_t tt_pool_attention_fused_workspace_bytes(int B, int S, int D, int H);
+int tt_pool_attention_fused(const float* x, const float* w,
+                            const float* W1, const float* b1, const float* W2, const float* b2, int H,
+                            float* out, int B, int S, int D,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Exact inner-product index  (reference: src/inference/vector_db.py over faiss.IndexFlatIP)

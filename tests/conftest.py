@@ -30,6 +30,17 @@ def native_lib():
 
 
 def rel_err(a, b):
+    """Norm-wise: max|a-b| / max|b| (the whole tensor's largest element is the scale)."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def elem_rel_err(a, b, floor_frac=0.1):
+    """Element-wise: max over elements of |a-b| / max(|b|, floor), floor = floor_frac * rms of that ROW of b (elements
+    far below the row's typical magnitude are held to an absolute tolerance instead of an unbounded relative one)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    rms = np.sqrt((b * b).mean(axis=-1, keepdims=True))
+    floor = np.maximum(floor_frac * rms, 1e-30)
+    return float((np.abs(a - b) / np.maximum(np.abs(b), floor)).max())

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, golden, rel_err
+from conftest import GOLDEN, elem_rel_err, golden, rel_err
 from oracle import buyer_tower_oracle as bo
 
 pytestmark = pytest.mark.gpu
@@ -37,6 +37,7 @@ def test_pool_matches_reference_golden(case, method):
         out = m(x, w)
     assert out.shape == g[method].shape and out.dtype == torch.float32 and out.is_cuda
     assert rel_err(out.cpu().numpy(), g[method]) < TOL
+    assert elem_rel_err(out.cpu().numpy(), g[method]) < TOL       # element-wise, floor = 0.1 * row rms
     if method == "attention":
         seq = m.encode_from_sequence(x[0], w[0])           # [S,D],[S] -> [1,D]
         assert tuple(seq.shape) == (1, g["x"].shape[2])
@@ -66,6 +67,59 @@ def test_pool_matches_oracle_seeded(B, S, D, H):
     out = m(xt, wt).detach().cpu().numpy()
     ref = bo.attention_aggregation(x.astype(np.float64), w.astype(np.float64), *[p.astype(np.float64) for p in params])
     assert rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("B,S,D,H,scale", [
+    (4096, 50, 384, 128, 1.0),      # C2
+    (4096, 1, 384, 128, 1.0),       # S = 1: 64 buyers per MMA tile
+    (600, 7, 384, 128, 1.0), (90, 100, 384, 128, 1.0), (20, 300, 384, 128, 1.0), (3, 2000, 384, 128, 1.0),
+    (300, 17, 64, 24, 1.0), (500, 33, 128, 100, 1.0), (257, 50, 256, 128, 1.0), (149, 50, 320, 77, 1.0),
+    (1000, 50, 384, 128, 20.0),     # x20 parameters: logits of order 10, softmax close to one-hot
+    (1000, 50, 384, 128, 1e-3),     # tiny activations: fp16 `lo` pieces go subnormal, absolute error stays ~1e-8
+])
+def test_fused_attention_matches_fp64_oracle(B, S, D, H, scale):
+    """tt_pool_attention_fused (one kernel: fp16 two-piece tensor-core MLP + softmax pooling + L2 norm) on shapes the
+    fused path takes (B*S >= 4096, D % 64 == 0, D <= 384, H <= 128) vs the fp64 restatement of buyer_tower.py:70-101."""
+    import two_tower_model_v2_b200 as pkg
+    rng = np.random.default_rng(B + S + D)
+    x = (rng.standard_normal((B, S, D)) * (scale if scale < 1 else 1.0)).astype(np.float32)
+    w = np.array([1.0, 5.0, 10.0], np.float32)[rng.choice(3, (B, S), p=[0.75, 0.18, 0.07])]
+    if S > 4:
+        w[0, S // 2:] = 0           # zero-weight events keep their softmax mass (no masking in the reference)
+        x[1, S // 2:] = 0           # zero-padded history
+    torch.manual_seed(B + S)
+    m = pkg.BuyerTower(D, "attention", H).to(dev())
+    if scale > 1:
+        with torch.no_grad():
+            for prm in m.attention.parameters():
+                prm.mul_(scale)
+    params = [p.detach().cpu().numpy().astype(np.float64) for p in m.attention.parameters()]
+    with torch.no_grad():
+        out = m(torch.from_numpy(x).to(dev()), torch.from_numpy(w).to(dev())).cpu().numpy()
+    ref = bo.attention_aggregation(x.astype(np.float64), w.astype(np.float64), *params)
+    assert rel_err(out, ref) < TOL and elem_rel_err(out, ref) < TOL, (rel_err(out, ref), elem_rel_err(out, ref))
+
+
+def test_fused_attention_out_of_fp16_range_is_recomputed_in_fp32():
+    """|x| * 16 > 65504 cannot be split into fp16 pieces: the kernel raises its device flag and the predicated fp32
+    kernel recomputes the whole call (no host sync); results still match the oracle, including the affected buyers."""
+    import two_tower_model_v2_b200 as pkg
+    rng = np.random.default_rng(77)
+    B, S, D, H = 200, 50, 384, 128
+    x = rng.standard_normal((B, S, D)).astype(np.float32)
+    x[17, 3, 100] = 9.0e4
+    x[60, :, :] *= 5000.0
+    w = np.array([1.0, 5.0, 10.0], np.float32)[rng.integers(0, 3, (B, S))]
+    torch.manual_seed(5)
+    m = pkg.BuyerTower(D, "attention", H).to(dev())
+    with torch.no_grad():
+        for prm in m.attention.parameters():
+            prm.mul_(1e-3)             # keep the huge rows' logits finite so that the comparison is meaningful
+    params = [p.detach().cpu().numpy().astype(np.float64) for p in m.attention.parameters()]
+    with torch.no_grad():
+        out = m(torch.from_numpy(x).to(dev()), torch.from_numpy(w).to(dev())).cpu().numpy()
+    ref = bo.attention_aggregation(x.astype(np.float64), w.astype(np.float64), *params)
+    assert np.isfinite(out).all() and rel_err(out, ref) < 1e-4      # fp32 arithmetic on 1e4-scale logits
 
 
 @pytest.mark.parametrize("method", ["weighted_avg", "attention"])
@@ -142,3 +196,41 @@ def test_backward_matches_reference_formulation(method):
         assert torch.allclose(a, b.grad, atol=1e-6, rtol=1e-4)
     with torch.no_grad():                                   # inference path unchanged: no graph, same numbers
         assert torch.equal(tower(x, w), out.detach())
+
+
+@pytest.mark.parametrize("method", ["weighted_avg", "attention"])
+@pytest.mark.parametrize("G,B,S,D", [(8, 257, 50, 384), (3, 1, 100, 384), (4, 40, 7, 64), (2, 1024, 50, 384)])
+def test_sharded_partial_pooling_matches_unsharded(method, G, B, S, D):
+    """Owner-computes pooling over a row-sharded item table (BASELINE config C5): per-shard partial records
+    (tt_pool_partial_gather) stacked as an all-gather would, merged by tt_pool_partial_merge, against the oracle
+    on the gathered rows and against the unsharded gather kernel."""
+    import two_tower_model_v2_b200 as pkg
+    from two_tower_model_v2_b200 import ops
+    rng = np.random.default_rng(G * 100 + B)
+    N = 6000
+    table = rng.standard_normal((N, D)).astype(np.float32)
+    table /= np.linalg.norm(table, axis=1, keepdims=True)
+    idx = rng.integers(0, N, (B, S))
+    idx[0, S // 2:] = -1                 # zero-padded tail
+    if B > 1:
+        idx[1, :] = N + 7                # a buyer with no valid row at all
+    w = np.array([1.0, 5.0, 10.0], np.float32)[rng.integers(0, 3, (B, S))]
+    w[0, S // 2:] = 0
+    torch.manual_seed(7)
+    m = pkg.BuyerTower(D, method).to(dev())
+    tt = torch.from_numpy(table).to(dev())
+    it, wt = torch.from_numpy(idx).to(dev()), torch.from_numpy(w).to(dev())
+    logits = m.precompute_item_logits(tt)
+    zero_logit = m.zero_row_logit() if method == "attention" else 0.0
+    parts = []
+    for g in range(G):
+        lo, hi = pkg.shard_bounds(N, G, g)
+        parts.append(ops.pool_partial_gather(tt[lo:hi].contiguous(), lo, N, g == 0,
+                                             None if logits is None else logits[lo:hi].contiguous(), zero_logit, it, wt))
+    out = ops.pool_partial_merge(torch.stack(parts), method == "attention").cpu().numpy()
+    x = bo.gather_rows(table, idx)
+    params = [p.detach().cpu().numpy() for p in m.parameters()] if method == "attention" else None
+    ref = bo.forward(x.astype(np.float64), w.astype(np.float64), method, None if params is None else [p.astype(np.float64) for p in params])
+    assert np.abs(out - ref).max() < TOL
+    single = m.forward_gather(tt, it, wt, logits).cpu().numpy()
+    assert np.abs(out - single).max() < 2e-6

@@ -13,10 +13,10 @@ The directory is named `two-tower-model-v2_b200`; import it as `two_tower_model_
 from .batcher import ArrayRows, MicroBatcher
 from .buyer_tower import BuyerTower
 from .config import get_event_weight
-from .retrieval import RetrievalPipeline
+from .retrieval import RetrievalPipeline, ShardedRetrievalPipeline
 from .sharded import ShardedFlatIPIndex, shard_bounds
 from .vector_db import (FlatIPIndex, VectorDatabase, read_flat_ip_file, read_native_shard, write_flat_ip_file,
                         write_native_shard)
 
-__all__ = ["BuyerTower", "VectorDatabase", "FlatIPIndex", "ShardedFlatIPIndex", "RetrievalPipeline", "MicroBatcher", "ArrayRows", "shard_bounds",
+__all__ = ["BuyerTower", "VectorDatabase", "FlatIPIndex", "ShardedFlatIPIndex", "RetrievalPipeline", "ShardedRetrievalPipeline", "MicroBatcher", "ArrayRows", "shard_bounds",
            "get_event_weight", "read_flat_ip_file", "write_flat_ip_file", "read_native_shard", "write_native_shard"]

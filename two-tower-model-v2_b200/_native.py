@@ -27,6 +27,12 @@ SIGNATURES = {
     "tt_attention_logits": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "tt_pool_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tt_pool_attention_gather": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tt_pool_partial_gather": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_float, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tt_pool_partial_merge": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "tt_pool_attention_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tt_pool_attention_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                        c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "tt_flat_pitch": (c_int64, [c_int]),
     "tt_flat_build": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "tt_flat_search_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),

@@ -46,9 +46,8 @@ class _FusedPool(torch.autograd.Function):
     def forward(ctx, x, w, *mlp):
         ctx.save_for_backward(x, w, *mlp)
         if mlp:
-            B, S, D = x.shape
-            logits = ops.attention_logits(x.view(B * S, D), mlp[0], mlp[1], mlp[2].reshape(-1), mlp[3]).view(B, S)
-            return ops.pool_attention(x, logits, w)
+            return ops.pool_attention_fused(x, w, mlp[0].contiguous(), mlp[1].contiguous(),
+                                            mlp[2].reshape(-1).contiguous(), mlp[3].contiguous())
         return ops.pool_weighted(x, w)
 
     @staticmethod
@@ -119,8 +118,7 @@ class BuyerTower(nn.Module):
             return _FusedPool.apply(x, w, l1.weight.float(), l1.bias.float(), l2.weight.float(), l2.bias.float()) \
                 .to(item_embeddings.dtype)
         W1, b1, W2, b2 = self._mlp_params(x.device)
-        logits = ops.attention_logits(x.view(B * S, D), W1, b1, W2, b2).view(B, S)
-        return ops.pool_attention(x, logits, w).to(item_embeddings.dtype)
+        return ops.pool_attention_fused(x, w, W1, b1, W2, b2).to(item_embeddings.dtype)
 
     def forward(self, item_embeddings: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
         """buyer_tower.py:103-122."""

@@ -299,3 +299,184 @@ extern "C" __attribute__((visibility("default"))) int tt_pool_attention_gather(c
   p.out = out; p.N = N; p.B = B; p.S = S; p.D = D;
   return launch_pool<true, true>(p, (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------------------------
+// Pooling out of a row-SHARDED item table (BASELINE config C5: the catalog, which is the item table of the
+// /retrieve path, is split over the GPUs).  Owner computes: every rank reduces the history rows it owns into a
+// partial record {acc[D], m, l, 0, 0} per buyer; ONE all-gather of the [B, D+4] records and a merge kernel finish the
+// pooling on every rank.  weighted_avg is linear (acc = sum w_s x_s, l = sum w_s over the positions the rank owns);
+// the attention softmax merges like an online softmax (m = max c_s, l = sum e^(c_s-m), acc = sum e^(c_s-m) x_s).
+// A position whose index is outside [0, N_total) is an all-zero row (zero-padded history): it adds nothing to acc
+// but keeps its weight / softmax mass, exactly as in the reference; the rank with owns_invalid = 1 accounts for it.
+namespace tt {
+
+struct PartialParams {
+  const float* table;      // this rank's rows [N_local, D]
+  const float* row_logits; // attention: logit of every LOCAL row [N_local]; NULL = weighted_avg
+  const int64_t* idx;      // [B,S] GLOBAL row ids
+  const float* w;          // [B,S]
+  float* partial;          // [B, D+4]: acc[D], m, l, 0, 0 (rows stay 16-byte aligned)
+  long long N_local, row_lo, N_total;
+  float zero_row_logit;
+  int owns_invalid;
+  int B, S, D;
+};
+
+template <int NV, bool ATTN>
+__global__ void __launch_bounds__(128)
+pool_partial_kernel(const PartialParams p) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= p.B) return;
+  const int S = p.S, D = p.D;
+  const int nvalid4 = D >> 2;
+  auto owned_c = [&](int s, long long& local_row, bool& own) -> float {
+    const long long bs = (long long)b * S + s;
+    const long long r = __ldg((const long long*)p.idx + bs);
+    const float wv = __ldg(p.w + bs);
+    const bool valid = (r >= 0 && r < p.N_total);
+    const bool mine = valid && r >= p.row_lo && r < p.row_lo + p.N_local;
+    own = mine || (!valid && p.owns_invalid);
+    local_row = mine ? (r - p.row_lo) : -1;
+    if (ATTN) return (mine ? __ldg(p.row_logits + (r - p.row_lo)) : p.zero_row_logit) * wv;
+    return wv;
+  };
+  float m = -INFINITY, l = 0.f;
+  if (ATTN) {
+    for (int s = lane; s < S; s += 32) { long long lr; bool own; const float c = owned_c(s, lr, own); if (own) m = fmaxf(m, c); }
+    m = warp_max(m);
+  }
+  float4 acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int U = 4;
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    const int s = s0 + lane;
+    float coef = 0.f;
+    long long lrow = -1;
+    if (s < S) {
+      bool own;
+      const float c = owned_c(s, lrow, own);
+      if (own) coef = ATTN ? expf(c - m) : c;
+      else lrow = -1;
+    }
+    l += coef;                                   // lane-private; reduced below
+    const int nrow = min(32, S - s0);
+    for (int j0 = 0; j0 < nrow; j0 += U) {
+      float4 buf[U][NV];
+      float cf[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u;
+        const int jj = (j < nrow) ? j : 0;
+        const float cj = __shfl_sync(0xffffffffu, coef, jj);
+        const long long rj = __shfl_sync(0xffffffffu, lrow, jj);
+        const bool ok = (j < nrow) && (rj >= 0);
+        cf[u] = ok ? cj : 0.f;
+        const float4* rp = reinterpret_cast<const float4*>(p.table + (ok ? rj : 0) * (long long)D);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c4 = v * 32 + lane;
+          buf[u][v] = (ok && c4 < nvalid4) ? ldg_stream(rp + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          acc[v].x = fmaf(buf[u][v].x, cf[u], acc[v].x);
+          acc[v].y = fmaf(buf[u][v].y, cf[u], acc[v].y);
+          acc[v].z = fmaf(buf[u][v].z, cf[u], acc[v].z);
+          acc[v].w = fmaf(buf[u][v].w, cf[u], acc[v].w);
+        }
+      }
+    }
+  }
+  l = warp_sum(l);
+  float4* op = reinterpret_cast<float4*>(p.partial + (long long)b * (D + 4));
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c4 = v * 32 + lane;
+    if (c4 < nvalid4) op[c4] = acc[v];
+  }
+  if (lane == 0) op[nvalid4] = make_float4(ATTN ? m : 0.f, l, 0.f, 0.f);
+}
+
+// partials f32 [G, B, D+4] -> out [B, D], one warp per buyer.
+__global__ void __launch_bounds__(128)
+pool_partial_merge_kernel(const float* __restrict__ pg, int G, int attention, float* __restrict__ out, int B, int D) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const long long stride = (long long)B * (D + 4);
+  const float* base = pg + (long long)b * (D + 4);
+  float M = -INFINITY;
+  if (attention)
+    for (int g = 0; g < G; ++g) { const float lg = base[g * stride + D + 1]; if (lg > 0.f) M = fmaxf(M, base[g * stride + D]); }
+  float L = 0.f;
+  for (int g = 0; g < G; ++g) {
+    const float lg = base[g * stride + D + 1];
+    L += attention ? ((lg > 0.f) ? lg * expf(base[g * stride + D] - M) : 0.f) : lg;
+  }
+  const float denom = attention ? L : (L + 1e-8f);        // buyer_tower.py:59 / :92
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float y = 0.f;
+    for (int g = 0; g < G; ++g) {
+      const float lg = base[g * stride + D + 1];
+      const float sc = attention ? ((lg > 0.f) ? expf(base[g * stride + D] - M) : 0.f) : 1.f;
+      y = fmaf(base[g * stride + d], sc, y);
+    }
+    y /= denom;
+    out[(long long)b * D + d] = y;
+    ss += y * y;
+  }
+  ss = warp_sum(ss);
+  const float nrm = fmaxf(sqrtf(ss), 1e-12f);             // F.normalize eps, buyer_tower.py:66/:99
+  __syncwarp();
+  for (int d = lane; d < D; d += 32) out[(long long)b * D + d] /= nrm;
+}
+
+template <bool ATTN>
+static int launch_partial(const PartialParams& p, cudaStream_t st) {
+  const int grid = (p.B + 3) / 4;
+  const int nv = (p.D + 127) / 128;
+  switch (nv) {
+    case 1: pool_partial_kernel<1, ATTN><<<grid, 128, 0, st>>>(p); break;
+    case 2: pool_partial_kernel<2, ATTN><<<grid, 128, 0, st>>>(p); break;
+    case 3: pool_partial_kernel<3, ATTN><<<grid, 128, 0, st>>>(p); break;
+    case 4: pool_partial_kernel<4, ATTN><<<grid, 128, 0, st>>>(p); break;
+    case 5: case 6: pool_partial_kernel<6, ATTN><<<grid, 128, 0, st>>>(p); break;
+    default: pool_partial_kernel<8, ATTN><<<grid, 128, 0, st>>>(p); break;
+  }
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}
+
+}  // namespace tt
+
+extern "C" __attribute__((visibility("default"))) int tt_pool_partial_gather(const float* table, int64_t N_local, int64_t row_lo, int64_t N_total,
+                                                                int owns_invalid, const float* row_logits, float zero_row_logit,
+                                                                const int64_t* idx, const float* w, float* partial, int B, int S, int D,
+                                                                void* stream) {
+  TT_CHECK_ARG(table && idx && w && partial, "null pointer");
+  TT_CHECK_ARG(B >= 0 && S >= 1 && D >= 4 && D % 4 == 0 && D <= 1024, "need B >= 0, S >= 1, D % 4 == 0, 4 <= D <= 1024");
+  TT_CHECK_ARG(N_local >= 1 && row_lo >= 0 && N_total >= row_lo + N_local, "bad shard bounds");
+  TT_CHECK_ARG(((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(partial)) & 15) == 0, "table and partial must be 16-byte aligned");
+  if (B == 0) return TT_OK;
+  PartialParams p{};
+  p.table = table; p.row_logits = row_logits; p.idx = idx; p.w = w; p.partial = partial;
+  p.N_local = N_local; p.row_lo = row_lo; p.N_total = N_total; p.zero_row_logit = zero_row_logit;
+  p.owns_invalid = owns_invalid; p.B = B; p.S = S; p.D = D;
+  return row_logits ? launch_partial<true>(p, (cudaStream_t)stream) : launch_partial<false>(p, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int tt_pool_partial_merge(const float* partials_g, int G, int attention, float* out, int B, int D,
+                                                               void* stream) {
+  TT_CHECK_ARG(partials_g && out, "null pointer");
+  TT_CHECK_ARG(G >= 1 && B >= 0 && D >= 1, "need G >= 1, B >= 0, D >= 1");
+  if (B == 0) return TT_OK;
+  pool_partial_merge_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(partials_g, G, attention, out, B, D);
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}

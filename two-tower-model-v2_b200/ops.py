@@ -73,6 +73,23 @@ def pool_attention(x: torch.Tensor, logits: torch.Tensor, w: torch.Tensor) -> to
     return out
 
 
+@torch.library.custom_op("tt::pool_attention_fused", mutates_args=(), device_types="cuda")
+def pool_attention_fused(x: torch.Tensor, w: torch.Tensor, W1: torch.Tensor, b1: torch.Tensor, W2: torch.Tensor,
+                         b2: torch.Tensor) -> torch.Tensor:
+    """buyer_tower.py:70-101 in one kernel / one pass over x — x [B,S,D], w [B,S], MLP params -> [B,D]."""
+    B, S, D = x.shape
+    H = W1.shape[0]
+    lib = _native.load()
+    out = torch.empty((B, D), device=x.device, dtype=torch.float32)
+    ws = torch.empty(max(int(lib.tt_pool_attention_fused_workspace_bytes(max(B, 1), S, D, H)), 256), device=x.device,
+                     dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        _native.check(lib.tt_pool_attention_fused(x.data_ptr(), w.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(),
+                                                  b2.data_ptr(), H, out.data_ptr(), B, S, D, ws.data_ptr(), ws.numel(),
+                                                  _stream()), "tt_pool_attention_fused")
+    return out
+
+
 @torch.library.custom_op("tt::pool_attention_gather", mutates_args=(), device_types="cuda")
 def pool_attention_gather(table: torch.Tensor, row_logits: torch.Tensor, zero_row_logit: float,
                           idx: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
@@ -84,6 +101,32 @@ def pool_attention_gather(table: torch.Tensor, row_logits: torch.Tensor, zero_ro
                                                               float(zero_row_logit), idx.data_ptr(), w.data_ptr(),
                                                               out.data_ptr(), B, S, D, _stream()),
                       "tt_pool_attention_gather")
+    return out
+
+
+def pool_partial_gather(table: torch.Tensor, row_lo: int, n_total: int, owns_invalid: bool, row_logits, zero_row_logit: float,
+                        idx: torch.Tensor, w: torch.Tensor, partial: torch.Tensor = None) -> torch.Tensor:
+    """Owner-computes partial pooling over this rank's rows of a sharded item table -> partial f32 [B, D+4]
+    (tt_pool_partial_gather); row_logits None = weighted_avg."""
+    n_local, D = table.shape
+    B, S = idx.shape
+    if partial is None:
+        partial = torch.empty((B, D + 4), device=table.device, dtype=torch.float32)
+    with torch.cuda.device(table.device):
+        _native.check(_native.load().tt_pool_partial_gather(
+            table.data_ptr(), n_local, int(row_lo), int(n_total), 1 if owns_invalid else 0,
+            0 if row_logits is None else row_logits.data_ptr(), float(zero_row_logit), idx.data_ptr(), w.data_ptr(),
+            partial.data_ptr(), B, S, D, _stream()), "tt_pool_partial_gather")
+    return partial
+
+
+def pool_partial_merge(partials_g: torch.Tensor, attention: bool) -> torch.Tensor:
+    """All-gathered partials f32 [G, B, D+4] -> L2-normalised buyer embeddings [B, D] (tt_pool_partial_merge)."""
+    G, B, D2 = partials_g.shape
+    out = torch.empty((B, D2 - 4), device=partials_g.device, dtype=torch.float32)
+    with torch.cuda.device(partials_g.device):
+        _native.check(_native.load().tt_pool_partial_merge(partials_g.data_ptr(), G, 1 if attention else 0, out.data_ptr(),
+                                                           B, D2 - 4, _stream()), "tt_pool_partial_merge")
     return out
 
 
@@ -168,4 +211,4 @@ def shard_merge(gathered: torch.Tensor, off_scores: int, off_ids: int, off_bound
 
 
 __all__ = ["shard_merge", "flat_build", "flat_search", "flat_search_exact", "pool_weighted", "pool_weighted_gather", "attention_logits", "pool_attention",
-           "pool_attention_gather", "topk_merge", "_f32c", "_stream"]
+           "pool_attention_gather", "pool_attention_fused", "pool_partial_gather", "pool_partial_merge", "topk_merge", "_f32c", "_stream"]

@@ -96,3 +96,82 @@ class RetrievalPipeline:
         pids = self.db.product_ids
         n = len(pids)
         return [[(pids[i], s) for i, s in zip(ri, rs) if 0 <= i < n] for rs, ri in zip(scores.tolist(), ids.tolist())]
+
+
+class ShardedRetrievalPipeline:
+    """The `/retrieve` path over a catalog sharded across GPUs (BASELINE config C5; one process per GPU, every rank
+    calls the same methods with the same batch - the front-end replicates or slices requests as it does queries).
+
+    The item table of the pooling IS the sharded catalog (fp32 rows `xn` of the local FlatIPIndex), so the pooling is
+    owner-computes: each rank reduces the history rows it owns into a partial record per buyer (tt_pool_partial_gather:
+    weighted sums are linear, the attention softmax merges like an online softmax), ONE all-gather of the [B, D+4]
+    records over NVLink (our peer-memory push/wait kernels, or NCCL) and tt_pool_partial_merge give every rank the
+    buyer embeddings, which go straight into the sharded exact search (ShardedFlatIPIndex.search_async).
+    History row ids are GLOBAL catalog rows; ids outside [0, n_total) pool as all-zero rows (zero-padded history).
+    """
+
+    def __init__(self, buyer_tower: BuyerTower, sharded_index, group=None):
+        import torch.distributed as dist
+        self.tower = buyer_tower
+        self.sharded = sharded_index
+        self.local = sharded_index.local
+        self.group = group
+        self.n_total = sharded_index.n_total
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.attention = buyer_tower.aggregation_method == "attention"
+        if buyer_tower.aggregation_method not in ("attention", "weighted_avg"):
+            raise ValueError(f"Unknown aggregation method: {buyer_tower.aggregation_method}")
+        self.table = self.local.xn
+        self.row_lo = int(self.local.id_offset)
+        self.item_logits = buyer_tower.precompute_item_logits(self.table)      # logits of the LOCAL rows
+        self.zero_row_logit = buyer_tower.zero_row_logit() if self.attention else 0.0
+        self._bufs = {}
+
+    def encode_device(self, indices: torch.Tensor, weights: torch.Tensor, k_for_exchange: int = 100) -> torch.Tensor:
+        """history rows i64 [B,S] (global ids) + weights f32 [B,S], replicated on every rank -> buyer embeddings [B,D]
+        on every rank."""
+        import torch.distributed as dist
+        from . import ops
+        idx = indices.to(device=self.table.device, dtype=torch.int64).contiguous()
+        w = ops._f32c(weights.to(self.table.device), "weights")
+        B, D = idx.shape[0], self.table.shape[1]
+        key = (B, self.world)
+        bufs = self._bufs.get(key)
+        if bufs is None:
+            if len(self._bufs) > 8:
+                self._bufs.clear()
+            bufs = self._bufs[key] = (torch.empty((B, D + 4), device=self.table.device, dtype=torch.float32),
+                                      torch.empty((self.world, B, D + 4), device=self.table.device, dtype=torch.float32))
+        partial, gathered = bufs
+        ops.pool_partial_gather(self.table, self.row_lo, self.n_total, self.rank == 0, self.item_logits,
+                                self.zero_row_logit, idx, w, partial)
+        if self.world == 1:
+            gathered = partial.view(1, B, D + 4)
+        else:
+            p2p = None
+            if self.table.is_cuda:
+                from .sharded import record_layout
+                p2p = self.sharded._p2p_for(B, k_for_exchange, self.table.device, self.world, record_layout(B, k_for_exchange))
+            if p2p is not None and len(p2p.nbytes) > 2:
+                status = self.sharded._bufs.setdefault(("status", B, k_for_exchange, self.world),
+                                                       torch.zeros(2, dtype=torch.int32, device=self.table.device))
+                g = p2p.all_gather(2, partial.view(torch.uint8).view(-1), status)
+                gathered = g.view(torch.float32).view(self.world, B, D + 4)
+            else:
+                dist.all_gather_into_tensor(gathered.view(-1), partial.view(-1), group=self.group)
+        return ops.pool_partial_merge(gathered, self.attention)
+
+    def retrieve_device_async(self, indices: torch.Tensor, weights: torch.Tensor, k: int) -> PendingSearch:
+        k = min(k, self.n_total)                                                       # vector_db.py:159
+        return self.sharded.search_async(self.encode_device(indices, weights, k), k)
+
+    def retrieve_host_async(self, idx_host: torch.Tensor, w_host: torch.Tensor, k: int) -> PendingSearch:
+        """Pinned host tensors in (history rows / weights of the WHOLE batch, the same on every rank), numpy out."""
+        dev = self.table.device
+        pending = self.retrieve_device_async(idx_host.to(dev, non_blocking=True), w_host.to(dev, non_blocking=True), k)
+
+        def finish():
+            s, i, n_bad = pending.result()
+            return s.cpu().numpy(), i.cpu().numpy(), n_bad
+        return PendingSearch(finish)

@@ -272,7 +272,8 @@ class ShardedFlatIPIndex:
         self._p2p.clear()
 
     def _p2p_for(self, nq: int, k: int, device, world: int, lay: RecordLayout):
-        """The P2PExchange for this (nq, k) shape (channel 0: top-r lists, channel 1: result records), or None
+        """The P2PExchange for this (nq, k) shape (channel 0: top-r lists, channel 1: result records, channel 2: pooling
+        partials of the sharded /retrieve path), or None
         when the NCCL path is to be used.  Created collectively: every rank reaches this with the same shape."""
         if world == 1 or device.type != "cuda" or self.exchange == "nccl" or self._merge is not _merge_cuda:
             self.exchange_used = self.exchange_used or "nccl"
@@ -291,7 +292,11 @@ class ShardedFlatIPIndex:
                     old.close()
             ok, ex = 1, None
             try:
-                ex = P2PExchange([nq * TT_SHARD_TOPR * 4, lay.nbytes], device, self.group)
+                d = getattr(self.local, "d", None)
+                chans = [nq * TT_SHARD_TOPR * 4, lay.nbytes]
+                if d is not None and d % 4 == 0:     # channel 2: pooling partials [nq, d+4] f32 of the sharded /retrieve path
+                    chans.append(nq * (d + 4) * 4)
+                ex = P2PExchange(chans, device, self.group)
             except Exception as e:     # IPC not permitted, no peer access, ...
                 if self.exchange == "p2p":
                     raise
