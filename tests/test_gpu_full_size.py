@@ -55,9 +55,20 @@ def oracle_topk_chunked(xn_dev, qn, k, chunk=1 << 20):
 
 @pytest.mark.parametrize("name,N,D,nqs", CASES, ids=[c[0] for c in CASES])
 def test_benched_sizes_match_exact_path_torch_checker_and_oracle(name, N, D, nqs):
+    import time
     torch.cuda.empty_cache()
+    t0 = time.perf_counter()
     index, _, _ = bench.make_shard(N, D, 1, 0)
     dev = index.xn.device
+    torch.cuda.synchronize()
+
+    def lap(what):
+        nonlocal t0
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        print(f"[{name}] {what}: {t - t0:.2f} s", flush=True)
+        t0 = t
+    lap("catalog")
     try:
         for nq in nqs:
             q = torch.randn((nq, D), device=dev, generator=torch.Generator(device="cuda").manual_seed(4321))
@@ -68,21 +79,25 @@ def test_benched_sizes_match_exact_path_torch_checker_and_oracle(name, N, D, nqs
             # i.i.d. catalogs: the planner's thresholds must certify (nearly) everything on the tensor-core path
             assert n_bad <= max(1, nq // 1000), f"{name} nq={nq}: {n_bad} queries fell back to the exact path"
             assert bool((s[:, 1:] <= s[:, :-1]).all()) and int(i.min()) >= 0 and int(i.max()) < N
+            lap(f"nq={nq} search")
             # (1) every query vs the independent fp32 checker
             ts, ti = bench.torch_flat_topk(index.xn, q, K)
             rep = bench.compare_topk_device(s, i, ts, ti)
             assert rep["ok"], f"{name} nq={nq} vs torch sgemm+topk: {rep}"
+            lap(f"nq={nq} torch checker ({rep['queries_with_id_differences']} queries differ inside ties)")
             # (2) sampled queries vs the library's exact fp32 path
             sel = torch.linspace(0, nq - 1, min(nq, 64), device=dev).long()
             es, ei = index.search_exact_device(q[sel].contiguous(), K)
             rep = bench.compare_topk_device(s[sel], i[sel], es, ei)
             assert rep["ok"], f"{name} nq={nq} vs tt_flat_search_exact: {rep}"
+            lap(f"nq={nq} exact path")
             # (3) sampled queries vs the CPU oracle
             sub = torch.linspace(0, nq - 1, min(nq, 8), device=dev).long()
             qn = fo.normalize_rows(q[sub].cpu().numpy())
             rs, ri = oracle_topk_chunked(index.xn, qn, K)
             ok, msg = fo.compare_topk(s[sub].cpu().numpy(), i[sub].cpu().numpy(), rs, ri, _DeviceRows(index.xn), qn)
             assert ok, f"{name} nq={nq} vs CPU oracle: {msg}"
+            lap(f"nq={nq} CPU oracle")
     finally:
         del index
         torch.cuda.empty_cache()

@@ -71,6 +71,55 @@ def test_flat_file_round_trip(tmp_path):
     p.write_bytes(raw[:-4])
     with pytest.raises(ValueError, match="truncated"):
         read_flat_ip_file(str(p))
+    p.write_bytes(raw + b"\0\0\0\0")
+    with pytest.raises(ValueError, match="unexpected bytes"):
+        read_flat_ip_file(str(p))
+
+
+def test_flat_file_is_byte_exact_faiss_indexflatip_layout(tmp_path):
+    """Fence for the on-disk format (reference: faiss.write_index / read_index at vector_db.py:117,77).  The fixture is
+    assembled here field by field in the order upstream faiss serialises an IndexFlatIP - faiss/impl/index_write.cpp:
+    write_index(): WRITE1(fourcc("IxFI")); write_index_header(): WRITE1(d) [int], WRITE1(ntotal) [idx_t = int64],
+    WRITE1(dummy = 1 << 20) twice [idx_t], WRITE1(is_trained) [bool], WRITE1(metric_type) [int, METRIC_INNER_PRODUCT = 0];
+    then WRITEXBVECTOR(codes) (faiss/impl/io_macros.h): size_t count of 4-byte units, raw bytes - independently of
+    the struct string the writer uses.  faiss itself is not installable in this image: the layout is restated, not
+    verified against a real file (INTEGRATION.md says so), which is why the reader rejects anything else."""
+    import struct
+    rows = (np.arange(3 * 5, dtype=np.float32).reshape(3, 5) - 7.0) / 3.0
+    fixture = b"".join([
+        b"IxFI",                                 # fourcc: 'I' | 'x' << 8 | 'F' << 16 | 'I' << 24, little endian
+        struct.pack("<i", 5),                    # int d
+        struct.pack("<q", 3),                    # idx_t ntotal
+        struct.pack("<q", 1 << 20),              # idx_t dummy
+        struct.pack("<q", 1 << 20),              # idx_t dummy
+        struct.pack("<?", True),                 # bool is_trained
+        struct.pack("<i", 0),                    # MetricType metric_type = METRIC_INNER_PRODUCT
+        struct.pack("<Q", 3 * 5),                # size_t codes.size() / 4
+        rows.astype("<f4").tobytes(),            # codes: ntotal * d floats, row-major
+    ])
+    assert len(fixture) == 45 + 60
+    p = tmp_path / "fixture.faiss"
+    write_flat_ip_file(str(p), rows)
+    assert p.read_bytes() == fixture, "writer must produce the faiss IndexFlatIP byte stream"
+    p.write_bytes(fixture)
+    assert np.array_equal(read_flat_ip_file(str(p)), rows)
+    # everything else is refused loudly: other index types, other metrics, size mismatches
+    for tag in (b"IxF2", b"IwFl", b"IxMp", b"ABCD"):
+        p.write_bytes(tag + fixture[4:])
+        with pytest.raises(ValueError, match="not an IndexFlatIP"):
+            read_flat_ip_file(str(p))
+    bad_metric = fixture[:33] + struct.pack("<i", 1) + fixture[37:]
+    p.write_bytes(bad_metric)
+    with pytest.raises(ValueError, match="inconsistent"):
+        read_flat_ip_file(str(p))
+    bad_count = fixture[:37] + struct.pack("<Q", 14) + fixture[45:]
+    p.write_bytes(bad_count)
+    with pytest.raises(ValueError, match="inconsistent"):
+        read_flat_ip_file(str(p))
+    db = pkg.VectorDatabase(embedding_dim=384)
+    p.write_bytes(fixture)
+    with pytest.raises(ValueError, match="Embedding dimension mismatch"):
+        db.load_index(str(p))
 
 
 def test_event_weights():
@@ -266,3 +315,27 @@ def test_native_shard_file_roundtrip_and_validation(tmp_path):
         read_native_shard(str(tmp_path / "bad"))
     with pytest.raises(ValueError, match="pitch"):
         write_native_shard(str(tmp_path / "x"), xn, xh[:, :100], stats)
+
+
+def test_micro_batcher_hands_out_array_rows_without_python_lists():
+    """MicroBatcher + ArrayRows: every caller gets its own row views truncated to its k (a batch_fn returning arrays
+    must resolve EVERY future of the batch)."""
+    import threading
+    calls = []
+
+    def batch_fn(payloads, k):
+        calls.append(len(payloads))
+        ids = np.stack([np.arange(k) + 100 * p for p in payloads])
+        return pkg.ArrayRows(ids, ids.astype(np.float32) / 7)
+    out = {}
+    with pkg.MicroBatcher(batch_fn, max_batch=8, max_wait_ms=20.0) as mb:
+        def client(c):
+            out[c] = mb(c, 3 + c % 4)
+        ths = [threading.Thread(target=client, args=(c,)) for c in range(20)]
+        [t.start() for t in ths]
+        [t.join(timeout=30) for t in ths]
+        assert not any(t.is_alive() for t in ths), "a caller never got its result"
+    for c in range(20):
+        ids, scores = out[c]
+        assert len(out[c]) == 3 + c % 4 and ids[0] == 100 * c and np.allclose(scores, ids / 7)
+    assert sum(calls) == 20 and max(calls) <= 8

@@ -20,9 +20,27 @@ from concurrent.futures import Future
 from typing import Any, Callable, List, Optional, Sequence, Tuple
 
 
+class ArrayRow:
+    """One request's result as array views: `.ids` i64 [k], `.scores` f32 [k]; `row[:k]` truncates both, and
+    `ids, scores = row` unpacks."""
+    __slots__ = ("ids", "scores")
+
+    def __init__(self, ids, scores):
+        self.ids, self.scores = ids, scores
+
+    def __getitem__(self, sl):
+        return ArrayRow(self.ids[sl], self.scores[sl])
+
+    def __len__(self):
+        return len(self.ids)
+
+    def __iter__(self):
+        return iter((self.ids, self.scores))
+
+
 class ArrayRows:
-    """Batched results as two arrays (ids i64 [B,k], scores f32 [B,k]) that MicroBatcher can hand out per request
-    without building Python lists: `rows[r][:k]` is a view pair `(ids[r,:k], scores[r,:k])` (`.ids`, `.scores`)."""
+    """Batched results as two arrays (ids i64 [B,k], scores f32 [B,k]) that MicroBatcher hands out per request
+    without building Python lists: a sequence of B `ArrayRow` views."""
     __slots__ = ("ids", "scores")
 
     def __init__(self, ids, scores):
@@ -32,10 +50,10 @@ class ArrayRows:
         return len(self.ids)
 
     def __getitem__(self, r):
-        return ArrayRows(self.ids[r], self.scores[r])
+        return ArrayRow(self.ids[r], self.scores[r])
 
     def __iter__(self):
-        return iter((self.ids, self.scores))
+        return (ArrayRow(self.ids[r], self.scores[r]) for r in range(len(self.ids)))
 
 
 class MicroBatcher:

@@ -92,8 +92,7 @@ static int flat_search_impl(const float* q, int nq, const float* Xn, const void*
   TT_CHECK_ARG(K >= 1 && K <= N && K <= TT_FLAT_MAX_K, "need 1 <= K <= min(N, TT_FLAT_MAX_K)");
   TT_CHECK_ARG((reinterpret_cast<uintptr_t>(Xh) & 15) == 0, "Xh must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  TT_CHECK_CUDA(cudaMemsetAsync(n_uncertified, 0, sizeof(int32_t), st));
-  if (nq == 0) return TT_OK;
+  if (nq == 0) { TT_CHECK_CUDA(cudaMemsetAsync(n_uncertified, 0, sizeof(int32_t), st)); return TT_OK; }
 
   const ScanPlan pl = make_scan_plan(N, D, nq, K);
   TT_CHECK_ARG(workspace != nullptr, "null workspace");
@@ -101,6 +100,7 @@ static int flat_search_impl(const float* q, int nq, const float* Xn, const void*
   if (pl.route_exact || !pl.supported) {
     // K is too large a fraction of N for a sampled threshold, or the rows are too wide for the resident-query
     // scan (D > 1024): the fp32 exact path serves the batch.
+    TT_CHECK_CUDA(cudaMemsetAsync(n_uncertified, 0, sizeof(int32_t), st));
     fill_int_kernel<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, 1);
     TT_CHECK_LAUNCH();
     if (bound) {   // the exact path scores every row: nothing is left unbounded
@@ -122,7 +122,7 @@ static int flat_search_impl(const float* q, int nq, const float* Xn, const void*
   void* cand = ws + w.cand;
   float* sample = reinterpret_cast<float*>(ws + w.sample);
 
-  if (int e = launch_prep_queries(q, nq, pl.nq_pad, D, pl.Dp, stats, qn, qh, eps, st)) return e;
+  if (int e = launch_prep_queries(q, nq, pl.nq_pad, D, pl.Dp, stats, qn, qh, eps, n_uncertified, st)) return e;
   if (int e = launch_scan(pl, qh, Xh, N, nq, thr, cnt, cand, sample, st)) return e;
   return launch_finalize(pl, qn, Xn, N, D, nq, K, id_offset, thr, eps, cnt, cand, scores,
                          reinterpret_cast<long long*>(ids), flags, n_uncertified, bound, st);
@@ -175,7 +175,7 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_shard_sample(const
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   if (int e = launch_prep_queries(q, nq, pl.nq_pad, D, pl.Dp, stats, reinterpret_cast<float*>(ws + w.qn), ws + w.qh,
-                                  reinterpret_cast<float*>(ws + w.eps), st)) return e;
+                                  reinterpret_cast<float*>(ws + w.eps), nullptr, st)) return e;
   return launch_sample(pl, ws + w.qh, Xh, N_local, nq, nullptr, topr, reinterpret_cast<float*>(ws + w.sample), st);
 }
 
@@ -192,13 +192,12 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_shard_search(int n
   const SearchWs w = search_ws_layout(pl, D, nq);
   if (workspace_bytes < w.total) { set_error("tt_flat_shard_search: workspace too small"); return TT_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
-  TT_CHECK_CUDA(cudaMemsetAsync(n_uncertified, 0, sizeof(int32_t), st));
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   float* qn = reinterpret_cast<float*>(ws + w.qn);
   float* eps = reinterpret_cast<float*>(ws + w.eps);
   float* thr = reinterpret_cast<float*>(ws + w.thr);
   unsigned int* cnt = reinterpret_cast<unsigned int*>(ws + w.cnt);
-  if (int e = launch_select_gathered(topr_g, G, nq, pl.sample_rank, thr, st)) return e;
+  if (int e = launch_select_gathered(topr_g, G, nq, pl.sample_rank, thr, n_uncertified, st)) return e;
   if (int e = launch_main_scan(pl, ws + w.qh, Xh, N_local, nq, thr, cnt, ws + w.cand, st)) return e;
   return launch_finalize(pl, qn, Xn, N_local, D, nq, K, id_offset, thr, eps, cnt, ws + w.cand, scores,
                          reinterpret_cast<long long*>(ids), flags, n_uncertified, bound, st);
@@ -251,7 +250,7 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_scan_scores(const 
   void* cand = ws + w.cand;
   float* sample = reinterpret_cast<float*>(ws + w.sample);
   TT_CHECK_CUDA(cudaMemsetAsync(out, 0xFF, (size_t)nq * N * sizeof(float), st));   // NaN = "row never reported"
-  if (int e = launch_prep_queries(q, nq, pl.nq_pad, D, pl.Dp, stats, qn, qh, eps, st)) return e;
+  if (int e = launch_prep_queries(q, nq, pl.nq_pad, D, pl.Dp, stats, qn, qh, eps, nullptr, st)) return e;
   if (int e = launch_scan(pl, qh, Xh, N, nq, thr, cnt, cand, sample, st)) return e;
   scatter_scores_kernel<<<dim3(64, nq), 256, 0, st>>>(cnt, reinterpret_cast<const uint2*>(cand), pl.main_slices, pl.seg_cap, N, out);
   TT_CHECK_LAUNCH();

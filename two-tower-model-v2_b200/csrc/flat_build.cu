@@ -101,7 +101,10 @@ flat_build_kernel(const float* __restrict__ X, long long rows, int D, int Dp,
 __global__ void __launch_bounds__(256)
 flat_prep_queries_kernel(const float* __restrict__ q, int nq, int nq_pad, int D, int Dp,
                          const float* __restrict__ stats,
-                         float* qn, __nv_bfloat16* qh, float* eps) {
+                         float* qn, __nv_bfloat16* qh, float* eps, int* zero_me) {
+  pdl_trigger();
+  pdl_wait();      // the previous search on this stream may still be reading this workspace
+  if (zero_me && blockIdx.x == 0 && threadIdx.x == 0) *zero_me = 0;     // n_uncertified of this call (was a memset)
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= nq_pad) return;
@@ -144,11 +147,11 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_build(const float*
 
 namespace tt {
 int launch_prep_queries(const float* q, int nq, int nq_pad, int D, int Dp, const float* stats,
-                        float* qn, void* qh, float* eps, cudaStream_t st) {
+                        float* qn, void* qh, float* eps, int* zero_me, cudaStream_t st) {
   const int grid = (nq_pad + 7) / 8;
-  flat_prep_queries_kernel<<<grid, 256, 0, st>>>(q, nq, nq_pad, D, Dp, stats, qn,
-                                                 reinterpret_cast<__nv_bfloat16*>(qh), eps);
-  TT_CHECK_LAUNCH();
+  count_launch();
+  TT_CHECK_CUDA(launch_pdl(flat_prep_queries_kernel, dim3(grid), dim3(256), 0, st, q, nq, nq_pad, D, Dp, stats, qn,
+                           reinterpret_cast<__nv_bfloat16*>(qh), eps, zero_me));
   return TT_OK;
 }
 }  // namespace tt

@@ -32,8 +32,9 @@ struct ScanPlan {
 
 ScanPlan make_scan_plan(long long N, int D, int nq, int K);
 
+// zero_me (may be NULL): an int the kernel sets to 0 (the call's n_uncertified counter)
 int launch_prep_queries(const float* q, int nq, int nq_pad, int D, int Dp, const float* stats,
-                        float* qn, void* qh, float* eps, cudaStream_t st);
+                        float* qn, void* qh, float* eps, int* zero_me, cudaStream_t st);
 
 // sample pass (if plan.use_threshold) + threshold selection + main scan
 int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq,
@@ -43,7 +44,7 @@ int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N,
 ScanPlan make_shard_plan(long long N_local, long long N_total, int D, int nq, int K, bool* global_ok);
 int launch_sample(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr, float* topr,
                   float* sample_buf, cudaStream_t st);
-int launch_select_gathered(const float* topr_g, int G, int nq, int r, float* thr, cudaStream_t st);
+int launch_select_gathered(const float* topr_g, int G, int nq, int r, float* thr, int* zero_me, cudaStream_t st);
 int launch_main_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr,
                      unsigned int* seg_cnt, void* cand, cudaStream_t st);
 

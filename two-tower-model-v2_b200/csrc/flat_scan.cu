@@ -156,6 +156,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
+  pdl_trigger();      // the next kernel of the search may be scheduled once every CTA of this grid has started
 
   // ---- work assignment ----------------------------------------------------------------------
   const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -190,6 +191,8 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   if (PAIR) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();         // barriers, TMEM and descriptors were set up under the previous kernel's tail; its outputs
+                      // (query block, thresholds) are visible from here on
 
   if (warp == 0) {
     // =========================== TMA producer ===============================================
@@ -413,6 +416,8 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // bitonic sort.
 __global__ void __launch_bounds__(256)
 select_threshold_kernel(const float* __restrict__ sample, int n, int npad, int r, float* thr) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float vals[];
   __shared__ float wmax[8];
   __shared__ int widx[8];
@@ -481,6 +486,8 @@ constexpr int SEL_WQ = 8;   // queries (warps) per CTA
 __global__ void __launch_bounds__(SEL_WQ * 32)
 select_threshold_tile_kernel(const float* __restrict__ sample, int slots, int ld, int nq, int r, float* __restrict__ thr,
                              float* __restrict__ topr, int topr_ld) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sv[];   // [SEL_WQ][slots]
   const int q0 = blockIdx.x * SEL_WQ;
   for (int e = threadIdx.x; e < slots * SEL_WQ; e += blockDim.x) {
@@ -528,9 +535,13 @@ select_threshold_tile_kernel(const float* __restrict__ sample, int slots, int ld
 // (gathered f32 [G, nq, SHARD_TOPR], the layout an all-gather of the per-rank lists produces): the same
 // threshold on every rank, estimated from a sample of the WHOLE catalog.  One warp per query.
 __global__ void __launch_bounds__(SEL_WQ * 32)
-select_threshold_gathered_kernel(const float* __restrict__ gathered, int G, int nq, int r, float* __restrict__ thr) {
+select_threshold_gathered_kernel(const float* __restrict__ gathered, int G, int nq, int r, float* __restrict__ thr,
+                                 int* zero_me) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sv[];   // [SEL_WQ][G * SHARD_TOPR]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (zero_me && blockIdx.x == 0 && threadIdx.x == 0) *zero_me = 0;     // n_uncertified of this call
   const int q = blockIdx.x * SEL_WQ + warp;
   if (q >= nq) return;
   const int n = G * SHARD_TOPR;
@@ -569,6 +580,8 @@ select_threshold_gathered_kernel(const float* __restrict__ gathered, int G, int 
 }
 
 __global__ void fill_kernel(float* p, int n, float v) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -592,7 +605,32 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 [rows, pitch] row-major, box = [box_rows, 64 columns], 128-byte swizzle, OOB rows read as 0.
+static int encode_tmap_bf16(CUtensorMap* m, const void* base, long long rows, int pitch, int box_rows);
+
+// A search call encodes four descriptors (query block + catalog, sample + main pass) that only depend on
+// (base, rows, pitch, box): a small per-thread cache saves the driver calls on the small-batch path, where the
+// host enqueue time is comparable to the device time.
 static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, int pitch, int box_rows) {
+  struct Entry { const void* base; long long rows; int pitch, box_rows; unsigned long long stamp; CUtensorMap map; };
+  constexpr int NE = 16;
+  static thread_local Entry cache[NE] = {};
+  static thread_local unsigned long long clock_ = 0;
+  int victim = 0;
+  for (int i = 0; i < NE; ++i) {
+    Entry& e = cache[i];
+    if (e.stamp && e.base == base && e.rows == rows && e.pitch == pitch && e.box_rows == box_rows) {
+      e.stamp = ++clock_;
+      *m = e.map;
+      return TT_OK;
+    }
+    if (e.stamp < cache[victim].stamp) victim = i;
+  }
+  if (int err = encode_tmap_bf16(m, base, rows, pitch, box_rows)) return err;
+  cache[victim] = Entry{base, rows, pitch, box_rows, ++clock_, *m};
+  return TT_OK;
+}
+
+static int encode_tmap_bf16(CUtensorMap* m, const void* base, long long rows, int pitch, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return TT_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
@@ -781,13 +819,15 @@ static int launch_scan_t(const CUtensorMap& tq, const CUtensorMap& tx, const Sca
   cfg.blockDim = dim3(SCAN_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   count_launch();
   TT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tx, sp));
   return TT_OK;
@@ -828,9 +868,9 @@ int launch_sample(const ScanPlan& pl, const void* qh, const void* Xh, long long 
   if (pl.sample_tile_max) {
     const size_t sm = (size_t)pl.sample_slots * SEL_WQ * sizeof(float);
     TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    select_threshold_tile_kernel<<<(nq + SEL_WQ - 1) / SEL_WQ, SEL_WQ * 32, sm, st>>>(
-        sample_buf, pl.sample_slots, pl.nq_pad, nq, topr ? min(pl.sample_rank, SHARD_TOPR) : pl.sample_rank, thr, topr,
-        SHARD_TOPR);
+    TT_CHECK_CUDA(launch_pdl(select_threshold_tile_kernel, dim3((nq + SEL_WQ - 1) / SEL_WQ), dim3(SEL_WQ * 32), sm, st,
+                             (const float*)sample_buf, pl.sample_slots, pl.nq_pad, nq,
+                             topr ? min(pl.sample_rank, SHARD_TOPR) : pl.sample_rank, thr, topr, (int)SHARD_TOPR));
   } else {
     TT_CHECK_ARG(topr == nullptr, "top-r lists need the tile sampling mode");
     const int nvals = pl.sample_slots * CHUNKS;
@@ -838,16 +878,17 @@ int launch_sample(const ScanPlan& pl, const void* qh, const void* Xh, long long 
     while (npad < nvals) npad <<= 1;
     const size_t sm = (size_t)npad * sizeof(float);
     TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    select_threshold_kernel<<<nq, 256, sm, st>>>(sample_buf, nvals, npad, pl.sample_rank, thr);
+    TT_CHECK_CUDA(launch_pdl(select_threshold_kernel, dim3(nq), dim3(256), sm, st, (const float*)sample_buf, nvals, npad,
+                             pl.sample_rank, thr));
   }
   TT_CHECK_LAUNCH();
   return TT_OK;
 }
 
-int launch_select_gathered(const float* topr_g, int G, int nq, int r, float* thr, cudaStream_t st) {
+int launch_select_gathered(const float* topr_g, int G, int nq, int r, float* thr, int* zero_me, cudaStream_t st) {
   const size_t sm = (size_t)SEL_WQ * G * SHARD_TOPR * sizeof(float);
   TT_CHECK_CUDA(cudaFuncSetAttribute(select_threshold_gathered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  select_threshold_gathered_kernel<<<(nq + SEL_WQ - 1) / SEL_WQ, SEL_WQ * 32, sm, st>>>(topr_g, G, nq, r, thr);
+  select_threshold_gathered_kernel<<<(nq + SEL_WQ - 1) / SEL_WQ, SEL_WQ * 32, sm, st>>>(topr_g, G, nq, r, thr, zero_me);
   TT_CHECK_LAUNCH();
   return TT_OK;
 }
@@ -869,8 +910,8 @@ int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N,
   if (pl.use_threshold) {
     if (int e = launch_sample(pl, qh, Xh, N, nq, thr, nullptr, sample_buf, st)) return e;
   } else {
-    fill_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thr, nq, -INFINITY);
-    TT_CHECK_LAUNCH();
+    count_launch();
+    TT_CHECK_CUDA(launch_pdl(fill_kernel, dim3((nq + 255) / 256), dim3(256), 0, st, thr, nq, -INFINITY));
   }
   return launch_main_scan(pl, qh, Xh, N, nq, thr, seg_cnt, cand, st);
 }

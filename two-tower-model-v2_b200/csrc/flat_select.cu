@@ -74,6 +74,8 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
                      int seg_cap, int cand_cap,
                      float* __restrict__ scores, long long* __restrict__ ids, int* __restrict__ flags,
                      int* __restrict__ n_uncertified, float* __restrict__ bound_out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char fsm[];
   unsigned long long* key = reinterpret_cast<unsigned long long*>(fsm);
   float* qs = reinterpret_cast<float*>(key + cand_cap);
@@ -307,10 +309,10 @@ int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long l
   TT_CHECK_ARG(pl.main_slices <= FINALIZE_MAX_SLICES, "too many catalog slices");
   const size_t smem = (size_t)pl.cand_cap * 8 + (size_t)D * 4 + 16;
   TT_CHECK_CUDA(cudaFuncSetAttribute(flat_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  flat_finalize_kernel<<<nq, FIN_THREADS, smem, st>>>(qn, Xn, N, D, K, id_offset, thr, eps, seg_cnt,
-                                                      reinterpret_cast<const uint2*>(cand), pl.main_slices, pl.seg_cap,
-                                                      pl.cand_cap, scores, ids, flags, n_uncertified, bound_out);
-  TT_CHECK_LAUNCH();
+  count_launch();
+  TT_CHECK_CUDA(launch_pdl(flat_finalize_kernel, dim3(nq), dim3(FIN_THREADS), smem, st, qn, Xn, N, D, K, id_offset, thr, eps,
+                           seg_cnt, reinterpret_cast<const uint2*>(cand), pl.main_slices, pl.seg_cap, pl.cand_cap, scores,
+                           ids, flags, n_uncertified, bound_out));
   return TT_OK;
 }
 

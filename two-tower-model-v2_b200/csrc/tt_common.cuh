@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 
 #include "../../include/tt_b200.h"
@@ -51,7 +52,36 @@ inline int num_sms() {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// The kernels of one search call form a chain on one stream.  Each is launched with the programmatic-stream-
+// serialization attribute, calls pdl_trigger() first thing (its successor may be scheduled as soon as every CTA of
+// this grid has started) and pdl_wait() before it touches global memory (returns once the predecessor grid has
+// completed and its writes are visible).  The successor's launch latency and prologue (barrier init, TMEM
+// allocation, descriptor prefetch) then hide under the predecessor's tail.  TT_B200_PDL=0 disables the attribute
+// (the device-side instructions are no-ops without it).
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("TT_B200_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -23,15 +23,24 @@ import torch
 from . import _native, ops
 
 # ---------------------------------------------------------------------------------------------
-# FAISS flat-index file layout [faiss-upstream, recalled; not verifiable here: faiss is absent]
-#   u32 fourcc "IxFI" | i32 d | i64 ntotal | i64 dummy(1<<20) | i64 dummy(1<<20) | u8 is_trained |
-#   i32 metric_type (0 = inner product) | u64 n_floats | f32[n_floats] row-major rows
+# FAISS flat-index file (`faiss.write_index` of an IndexFlatIP; reference call sites vector_db.py:77,117).
+# faiss is not vendored under /root/reference and not installable here, so the layout below restates upstream faiss
+# (faiss/impl/index_write.cpp: `write_index` -> fourcc "IxFI" for METRIC_INNER_PRODUCT, `write_index_header`
+# -> d, ntotal, two dummies (1 << 20), is_trained, metric_type; then the storage as `WRITEXBVECTOR(codes)` / in
+# releases before 1.7.1 `WRITEVECTOR(xb)`: a u64 count of 4-byte units followed by the raw fp32 rows; faiss/impl/io_macros.h)
+# and has NOT been checked against a file written by a real faiss (see INTEGRATION.md "Before production").  The
+# reader therefore refuses everything it does not recognise exactly, loudly, instead of guessing:
+#   u32 fourcc "IxFI" | i32 d | i64 ntotal | i64 dummy | i64 dummy | u8 is_trained | i32 metric_type (0 = inner
+#   product) | u64 n_floats (= ntotal * d) | f32[n_floats] row-major rows | end of file
 _FOURCC_IXFI = struct.unpack("<I", b"IxFI")[0]
 _HDR = struct.Struct("<IiqqqBiQ")   # 45 bytes, little endian, unpadded
+_OTHER_FAISS_FOURCC = {b"IxF2": "IndexFlatL2", b"IxFl": "IndexFlat (other metric)", b"IwFl": "IndexIVFFlat",
+                       b"IxMp": "IndexIDMap", b"IxM2": "IndexIDMap2", b"IHNf": "IndexHNSWFlat", b"IxPq": "IndexPQ",
+                       b"IwPQ": "IndexIVFPQ", b"IxSQ": "IndexScalarQuantizer", b"IxPT": "IndexPreTransform"}
 
 
 def write_flat_ip_file(path: str, rows: np.ndarray) -> None:
-    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    rows = np.ascontiguousarray(rows, dtype="<f4")
     n, d = rows.shape
     with open(path, "wb") as f:
         f.write(_HDR.pack(_FOURCC_IXFI, d, n, 1 << 20, 1 << 20, 1, 0, n * d))
@@ -39,15 +48,28 @@ def write_flat_ip_file(path: str, rows: np.ndarray) -> None:
 
 
 def read_flat_ip_file(path: str) -> np.ndarray:
+    import os
     with open(path, "rb") as f:
         hdr = f.read(_HDR.size)
         if len(hdr) != _HDR.size:
             raise ValueError(f"{path}: truncated flat index header")
-        fourcc, d, n, _, _, _, metric, nfl = _HDR.unpack(hdr)
+        fourcc, d, n, _, _, trained, metric, nfl = _HDR.unpack(hdr)
         if fourcc != _FOURCC_IXFI:
-            raise ValueError(f"{path}: not an IndexFlatIP file (fourcc {fourcc:#x})")
-        if metric != 0 or nfl != n * d or d <= 0 or n < 0:
-            raise ValueError(f"{path}: inconsistent flat index header (d={d}, ntotal={n}, floats={nfl}, metric={metric})")
+            tag = hdr[:4]
+            kind = _OTHER_FAISS_FOURCC.get(tag)
+            what = f"a faiss {kind} file" if kind else f"fourcc {tag!r}"
+            raise ValueError(f"{path}: not an IndexFlatIP file ({what}); only the flat inner-product index the reference "
+                             f"builds (faiss.IndexFlatIP, vector_db.py:48) is supported")
+        if metric != 0 or nfl != n * d or d <= 0 or n < 0 or trained not in (0, 1):
+            raise ValueError(f"{path}: inconsistent flat index header (d={d}, ntotal={n}, floats={nfl}, metric={metric}, "
+                             f"is_trained={trained})")
+        expect = _HDR.size + 4 * n * d
+        actual = os.fstat(f.fileno()).st_size
+        if actual < expect:
+            raise ValueError(f"{path}: truncated flat index payload ({actual} bytes, header promises {expect})")
+        if actual > expect:
+            raise ValueError(f"{path}: {actual - expect} unexpected bytes after the fp32 rows - not the plain IndexFlatIP "
+                             f"layout this reader knows; refusing to guess")
         data = np.fromfile(f, dtype="<f4", count=n * d)
     if data.size != n * d:
         raise ValueError(f"{path}: truncated flat index payload")
@@ -526,6 +548,9 @@ class VectorDatabase:
                    mapping_path: Optional[str] = None):
         """vector_db.py:63-98 — rows are taken verbatim from the file (no re-normalisation)."""
         rows = read_flat_ip_file(index_path)
+        if self.embedding_dim is not None and rows.shape[1] != self.embedding_dim:
+            # faiss would load it and fail at the first search; say so at load time
+            raise ValueError(f"Embedding dimension mismatch: expected {self.embedding_dim}, index file has {rows.shape[1]}")
         index = FlatIPIndex(rows.shape[1])
         index.add(rows, normalize=False)
         self.index = index
