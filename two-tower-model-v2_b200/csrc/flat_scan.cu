@@ -40,95 +40,11 @@
 #include "tt_common.cuh"
 #include "sm100_ptx.cuh"
 #include "flat_internal.cuh"
+#include "flat_scan_common.cuh"
 
 namespace tt {
 
 using namespace ptx;
-
-constexpr int SCAN_THREADS = 256;
-constexpr int BLOCK_N = 256;                    // catalog rows per tile
-constexpr int BLOCK_K = 64;                     // bf16 per K-block = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
-constexpr int MAX_STAGES = 8;
-constexpr int TMEM_COLS = 512;                  // 2 accumulator buffers x 256 fp32 columns
-constexpr int CHUNKS = BLOCK_N / 32;
-constexpr int BAR_BYTES = 256;                  // mbarriers + TMEM base pointer
-constexpr int SCRATCH_BYTES = 4 * 256;          // one 64-value row per epilogue warp (candidate extraction)
-
-struct ScanParams {
-  long long N;            // catalog rows
-  int nq;                 // valid queries
-  int num_kb;             // K-blocks per row (Dp / 64)
-  int num_kb_res;         // leading K-blocks of the query block that stay resident in shared memory; the
-                          // rest (D > 640 in pair mode) is streamed with the catalog, once per tile, from L2
-  int stage_bytes;        // ring stride: the catalog K-block, plus room for a query K-block when streaming
-  int num_stages;         // ring depth
-  int nqu;                // query units (query blocks, or query-block pairs)
-  int nslices;            // catalog slices
-  int num_slots;          // tiles to visit in total (main: all tiles; sample: sampled tiles)
-  int tile_stride;        // tile index = slot * tile_stride
-  // MAIN
-  const float* thr;       // [nq]
-  unsigned int* seg_cnt;  // [nq, nslices]
-  uint2* cand;            // [nq, nslices, seg_cap]  (score bits, row)
-  int seg_cap;
-  // SAMPLE
-  float* sample_out;      // chunk mode: [nq_pad, num_slots, 8] maxima of the 32-row chunks of every sampled tile
-                          // tile mode : [num_slots, sample_ld] maximum of every sampled tile (query fastest)
-  int sample_tile_max;    // 1 = tile mode
-  int sample_ld;          // tile mode: leading dimension (nq_pad)
-};
-
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3 (sm_100)
-  return r;
-}
-__device__ __forceinline__ float max_tree(const uint32_t (&v)[32]) {
-  float m[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) m[i] = max3(__uint_as_float(v[i]), __uint_as_float(v[i + 4]), __uint_as_float(v[i + 8]));
-#pragma unroll
-  for (int j = 12; j < 28; j += 8)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) m[i] = max3(m[i], __uint_as_float(v[j + i]), __uint_as_float(v[j + i + 4]));
-#pragma unroll
-  for (int i = 0; i < 4; ++i) m[i] = fmaxf(m[i], __uint_as_float(v[28 + i]));
-  return max3(fmaxf(m[0], m[1]), m[2], m[3]);
-}
-
-// Slow paths of the epilogue (warp-collective: every lane of the warp must call them).  They read
-// `ncols` consecutive accumulator columns starting at `taddr`, 8 at a time, in a rolled loop.
-__device__ __noinline__ void append_columns(uint32_t taddr, int ncols, float thr, uint32_t row_base, uint2* seg,
-                                            unsigned int& cnt, unsigned int seg_cap) {
-#pragma unroll 1
-  for (int c = 0; c < ncols; c += 8) {
-    uint32_t v[8];
-    __syncwarp();
-    tmem_ld_32x8(taddr + (uint32_t)c, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (c + j < ncols && __uint_as_float(v[j]) >= thr) {
-        if (cnt < seg_cap) seg[cnt] = make_uint2(v[j], row_base + (uint32_t)(c + j));
-        ++cnt;
-      }
-    }
-  }
-}
-__device__ __noinline__ float max_columns(uint32_t taddr, int ncols) {
-  float m = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < ncols; c += 8) {
-    uint32_t v[8];
-    __syncwarp();
-    tmem_ld_32x8(taddr + (uint32_t)c, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) if (c + j < ncols) m = fmaxf(m, __uint_as_float(v[j]));
-  }
-  return m;
-}
 
 template <int BLOCK_M, bool SAMPLE, bool PAIR>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
@@ -606,6 +522,10 @@ static EncodeTiledFn get_encode_fn() {
 
 // bf16 [rows, pitch] row-major, box = [box_rows, 64 columns], 128-byte swizzle, OOB rows read as 0.
 static int encode_tmap_bf16(CUtensorMap* m, const void* base, long long rows, int pitch, int box_rows);
+static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, int pitch, int box_rows);
+int make_tmap_bf16(void* tensor_map, const void* base, long long rows, int pitch, int box_rows) {
+  return make_tmap_bf16(reinterpret_cast<CUtensorMap*>(tensor_map), base, rows, pitch, box_rows);
+}
 
 // A search call encodes four descriptors (query block + catalog, sample + main pass) that only depend on
 // (base, rows, pitch, box): a small per-thread cache saves the driver calls on the small-batch path, where the
@@ -725,6 +645,29 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   pl.num_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
   const int cap_units = pl.pair ? sms / 2 : sms;
   pl.main_slices = pick_slices(pl.nqu, cap_units, pl.num_tiles);
+  // Large batches: queries in tensor memory (flat_scan_ts.cu).  2 blocks of 256 queries per CTA pair when both fit
+  // next to the two 64-column accumulator slots (Dp <= 384), else 1 (Dp <= 768).
+  pl.ts = false;
+  static const bool ts_on = [] { const char* e = getenv("TT_B200_SCAN_TS"); return !(e && e[0] == '0'); }();
+  if (pl.pair && pl.supported && nq > 256 && ts_on) {
+    const int qcols = pl.Dp / 2;
+    const int nqb2 = (2 * qcols + 128 <= TMEM_COLS) ? 2 : ((qcols + 128 <= TMEM_COLS) ? 1 : 0);
+    if (nqb2 > 0) {
+      pl.ts = true;
+      pl.ts_nqb = nqb2;
+      const int unit_q = 256 * nqb2;
+      pl.nq_pad = (nq + unit_q - 1) / unit_q * unit_q;
+      pl.nqb = pl.nq_pad / pl.block_m;
+      pl.nqu = pl.nqb / 2;                                   // the sample pass still runs 256-query pairs
+      pl.ts_nqu = pl.nq_pad / unit_q;
+      pl.ts_tiles = (int)((N + 63) / 64);
+      const int slot_bytes = pl.num_kb * 32 * 128;          // this CTA's half of a 64-row tile
+      pl.ts_slots = (budget) / slot_bytes;
+      if (pl.ts_slots > 8) pl.ts_slots = 8;
+      if (pl.ts_slots < 2) pl.ts = false;
+      else pl.main_slices = pick_slices(pl.ts_nqu, cap_units, pl.num_tiles);     // never more slices than 256-row tiles
+    }
+  }
 
   // Candidate budget and sampling plan.  We aim at ~T candidates per query: the threshold is read
   // among the 32-row chunk maxima of every `stride`-th tile at the rank r' = T * n_s / N (n_s =
@@ -784,7 +727,8 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   // if the catalog fits a candidate list, else the always-exact fp32 path.
   pl.route_exact = false;
   pl.use_threshold = reliable;
-  const long long slice_rows = ((long long)(pl.num_tiles + pl.main_slices - 1) / pl.main_slices) * BLOCK_N;
+  const long long slice_rows = pl.ts ? ((long long)(pl.ts_tiles + pl.main_slices - 1) / pl.main_slices) * 64
+                                     : ((long long)(pl.num_tiles + pl.main_slices - 1) / pl.main_slices) * BLOCK_N;
   if (!reliable) {
     pl.sample_stride = 1; pl.sample_slots = 1; pl.sample_rank = 1; pl.target = 0; pl.sample_tile_max = false;
     if (N <= FINALIZE_MAX_CAND) {
@@ -895,6 +839,7 @@ int launch_select_gathered(const float* topr_g, int G, int nq, int r, float* thr
 
 int launch_main_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr,
                      unsigned int* seg_cnt, void* cand, cudaStream_t st) {
+  if (pl.ts) return launch_main_scan_ts(pl, qh, Xh, N, nq, thr, seg_cnt, cand, st);
   CUtensorMap tq, tx;
   ScanParams sp;
   if (int e = make_scan_params(pl, qh, Xh, N, nq, thr, seg_cnt, cand, nullptr, &tq, &tx, &sp)) return e;
@@ -936,7 +881,8 @@ ScanPlan make_shard_plan(long long N_local, long long N_total, int D, int nq, in
   const int cap_units = pl.pair ? num_sms() / 2 : num_sms();
   pl.sample_slices = pick_slices(pl.nqu, cap_units, pl.sample_slots);
   // a shard may hold every candidate of a query (clustered catalogs): size its segments for the whole target
-  const long long slice_rows = ((long long)(pl.num_tiles + pl.main_slices - 1) / pl.main_slices) * BLOCK_N;
+  const long long slice_rows = pl.ts ? ((long long)(pl.ts_tiles + pl.main_slices - 1) / pl.main_slices) * 64
+                                     : ((long long)(pl.num_tiles + pl.main_slices - 1) / pl.main_slices) * BLOCK_N;
   long long seg = 4LL * pl.target / pl.main_slices;
   if (seg < 512) seg = 512;
   if (seg > pl.cand_cap) seg = pl.cand_cap;
