@@ -97,7 +97,12 @@ def test_fused_attention_matches_fp64_oracle(B, S, D, H, scale):
     with torch.no_grad():
         out = m(torch.from_numpy(x).to(dev()), torch.from_numpy(w).to(dev())).cpu().numpy()
     ref = bo.attention_aggregation(x.astype(np.float64), w.astype(np.float64), *params)
-    assert rel_err(out, ref) < TOL and elem_rel_err(out, ref) < TOL, (rel_err(out, ref), elem_rel_err(out, ref))
+    # Ill-conditioned cases (x20 parameters: logits of order 100 inside exp) are held to a small multiple of the error
+    # the fp32 arithmetic of the reference itself makes there (fp32 restatement vs fp64), never less than TOL.
+    ref32 = bo.attention_aggregation(x, w, *[p.astype(np.float32) for p in params])
+    tol_n = max(TOL, 4 * rel_err(ref32, ref))
+    tol_e = max(TOL, 4 * elem_rel_err(ref32, ref))
+    assert rel_err(out, ref) < tol_n and elem_rel_err(out, ref) < tol_e, (rel_err(out, ref), elem_rel_err(out, ref), tol_n, tol_e)
 
 
 def test_fused_attention_out_of_fp16_range_is_recomputed_in_fp32():

@@ -63,10 +63,13 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ qs, const fl
 //      c = max(scan threshold, cutoff), hence an fp32 score below c + eps.  If the K-th best rescored
 //      fp32 score f_K >= c + eps, no such row can enter the top-K: the result is exact.  Otherwise the
 //      query is flagged and the host re-runs it through the exact path.
-constexpr int FIN_THREADS = 256;
+constexpr int FIN_THREADS = 256;          // large batches: one 256-thread CTA per query, several CTAs per SM
+constexpr int FIN_THREADS_WIDE = 1024;    // small batches (fewer queries than SMs): the latency-bound phases of the
+                                          // single query (gather, fp32 rescoring of ~200 scattered rows) get 4x the warps
 constexpr float PRUNE_MARGIN = 1.5f;       // in units of eps; typical |bf16 - fp32| is ~eps/25
 constexpr int RANK_BY_COUNT_MAX = 1024;    // survivors up to this many are ranked by counting, else bitonic sort
 
+template <int FIN_THREADS>
 __global__ void __launch_bounds__(FIN_THREADS)
 flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn, long long N, int D, int K,
                      long long id_offset, const float* __restrict__ thr, const float* __restrict__ eps,
@@ -132,7 +135,7 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
     uint32_t prefix = 0u, mask = 0u;
     int kk = K;
     for (int shift = 24; shift >= 0; shift -= 8) {
-      s_hist[tid] = 0u;
+      if (tid < 256) s_hist[tid] = 0u;
       __syncthreads();
       for (int i = tid; i < n; i += FIN_THREADS) {
         const uint32_t u = (uint32_t)(key[i] >> 32);
@@ -308,11 +311,18 @@ int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long l
                     float* bound_out, cudaStream_t st) {
   TT_CHECK_ARG(pl.main_slices <= FINALIZE_MAX_SLICES, "too many catalog slices");
   const size_t smem = (size_t)pl.cand_cap * 8 + (size_t)D * 4 + 16;
-  TT_CHECK_CUDA(cudaFuncSetAttribute(flat_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   count_launch();
-  TT_CHECK_CUDA(launch_pdl(flat_finalize_kernel, dim3(nq), dim3(FIN_THREADS), smem, st, qn, Xn, N, D, K, id_offset, thr, eps,
-                           seg_cnt, reinterpret_cast<const uint2*>(cand), pl.main_slices, pl.seg_cap, pl.cand_cap, scores,
-                           ids, flags, n_uncertified, bound_out));
+  if (nq <= num_sms() / 2) {
+    TT_CHECK_CUDA(cudaFuncSetAttribute(flat_finalize_kernel<FIN_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TT_CHECK_CUDA(launch_pdl(flat_finalize_kernel<FIN_THREADS_WIDE>, dim3(nq), dim3(FIN_THREADS_WIDE), smem, st, qn, Xn, N, D, K,
+                             id_offset, thr, eps, seg_cnt, reinterpret_cast<const uint2*>(cand), pl.main_slices, pl.seg_cap,
+                             pl.cand_cap, scores, ids, flags, n_uncertified, bound_out));
+  } else {
+    TT_CHECK_CUDA(cudaFuncSetAttribute(flat_finalize_kernel<FIN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TT_CHECK_CUDA(launch_pdl(flat_finalize_kernel<FIN_THREADS>, dim3(nq), dim3(FIN_THREADS), smem, st, qn, Xn, N, D, K, id_offset,
+                             thr, eps, seg_cnt, reinterpret_cast<const uint2*>(cand), pl.main_slices, pl.seg_cap, pl.cand_cap,
+                             scores, ids, flags, n_uncertified, bound_out));
+  }
   return TT_OK;
 }
 
