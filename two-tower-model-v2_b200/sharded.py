@@ -81,13 +81,18 @@ class P2PExchange:
     """All-gather of fixed-size records over NVLink peer memory with our own kernels (tt_p2p_push /
     tt_p2p_wait) instead of NCCL.
 
-    Every rank owns one device buffer holding, per channel, a double-buffered receive area [2][G][nbytes] and
-    flags int32 [2][G].  The buffers are mapped into every rank through CUDA IPC handles exchanged once over
+    Every rank owns one device buffer holding, per channel, NSLOT receive areas [NSLOT][G][nbytes] and flags
+    int32 [NSLOT][G] (slot = sequence number mod NSLOT).  `push` and `wait` are separate so that a caller can defer
+    the wait: the pipelined sharded search pushes batch j's record, scans batch j+1 and only then waits for the
+    peers' records of batch j (by then they have long arrived).  With the 3-stage pipeline of ShardedFlatIPIndex a
+    slot is overwritten no earlier than three exchanges later, after a wait that proves every peer has consumed it.  The buffers are mapped into every rank through CUDA IPC handles exchanged once over
     the process group (tt_p2p_alloc / tt_p2p_open); afterwards an exchange is two kernel launches
     on the caller's stream and no host synchronisation: push my record into my slot on every peer and raise
     my sequence flag there; wait (one warp, acquire loads, bounded by a time-out) until every rank's flag for
     this sequence number is up.  `status[1]` turns non-zero if a wait timed out.
     """
+
+    NSLOT = 4
 
     def __init__(self, channel_bytes, device: torch.device, group=None, timeout_s: float = 20.0):
         from . import _native
@@ -105,11 +110,11 @@ class P2PExchange:
         off = 0
         for b in self.nbytes:
             self.recv_off.append(off)
-            off += 2 * G * b
+            off += self.NSLOT * G * b
             off = (off + 255) // 256 * 256
         for _ in self.nbytes:
             self.flag_off.append(off)
-            off += 2 * G * 4
+            off += self.NSLOT * G * 4
             off = (off + 255) // 256 * 256
         import ctypes
         self._ctypes = ctypes
@@ -186,34 +191,46 @@ class P2PExchange:
             self.lib.tt_p2p_free(self._ctypes.c_void_p(self.base))
         self.base, self.peer_base = None, []
 
-    def _ptrs(self, ch: int, parity: int):
-        key = (ch, parity)
+    def _ptrs(self, ch: int, slot: int):
+        key = (ch, slot)
         arr = self._ptr_arrays.get(key)
         if arr is None:
             G, b = self.world, self.nbytes[ch]
             c = self._ctypes
-            dst = (c.c_void_p * G)(*[p + self.recv_off[ch] + (parity * G + self.rank) * b for p in self.peer_base])
-            flg = (c.c_void_p * G)(*[p + self.flag_off[ch] + (parity * G + self.rank) * 4 for p in self.peer_base])
+            dst = (c.c_void_p * G)(*[p + self.recv_off[ch] + (slot * G + self.rank) * b for p in self.peer_base])
+            flg = (c.c_void_p * G)(*[p + self.flag_off[ch] + (slot * G + self.rank) * 4 for p in self.peer_base])
             arr = self._ptr_arrays[key] = (dst, flg)
         return arr
 
-    def all_gather(self, ch: int, src: torch.Tensor, status: torch.Tensor) -> torch.Tensor:
-        """src: this rank's record (uint8 [nbytes[ch]], 16-byte aligned) -> uint8 [G, nbytes[ch]] view of this
-        rank's receive buffer, valid for kernels enqueued after this call on the current stream."""
+    def push(self, ch: int, src: torch.Tensor) -> int:
+        """Copies this rank's record (uint8 [nbytes[ch]], 16-byte aligned) into its slot on every peer and raises its
+        sequence flag there (one kernel on the current stream).  Returns the sequence number to `wait` for."""
         G, b = self.world, self.nbytes[ch]
         assert src.numel() * src.element_size() == b
         self.seq[ch] += 1
         seq = self.seq[ch]
-        parity = seq & 1
-        dst, flg = self._ptrs(ch, parity)
+        dst, flg = self._ptrs(ch, seq % self.NSLOT)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             self.check(self.lib.tt_p2p_push(src.data_ptr(), b, dst, flg, G, seq, self.done[ch:ch + 1].data_ptr(), stream),
                        "tt_p2p_push")
-            my_flags = self.base + self.flag_off[ch] + parity * G * 4
+        return seq
+
+    def wait(self, ch: int, seq: int, status: torch.Tensor) -> torch.Tensor:
+        """One-warp kernel on the current stream: returns once every rank's record `seq` has landed here -> uint8
+        [G, nbytes[ch]] view of this rank's receive slot, valid for kernels enqueued after this call."""
+        G, b = self.world, self.nbytes[ch]
+        slot = seq % self.NSLOT
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            my_flags = self.base + self.flag_off[ch] + slot * G * 4
             self.check(self.lib.tt_p2p_wait(my_flags, G, seq, self.timeout_s, status[1:2].data_ptr(), stream), "tt_p2p_wait")
-        o = self.recv_off[ch] + parity * G * b
+        o = self.recv_off[ch] + slot * G * b
         return self.buf[o:o + G * b].view(G, b)
+
+    def all_gather(self, ch: int, src: torch.Tensor, status: torch.Tensor) -> torch.Tensor:
+        """push + wait back to back."""
+        return self.wait(ch, self.push(ch, src), status)
 
 
 class ShardedFlatIPIndex:
@@ -241,6 +258,8 @@ class ShardedFlatIPIndex:
         # "auto" tries p2p on CUDA and falls back to nccl if the IPC set-up fails.
         self.exchange = os.environ.get("TT_B200_EXCHANGE", exchange)
         self.exchange_used = None
+        self.pipelined = os.environ.get("TT_B200_SHARD_PIPELINE", "1") != "0"
+        self._inflight = []
 
     @property
     def ntotal(self) -> int:
@@ -266,6 +285,7 @@ class ShardedFlatIPIndex:
 
     def close(self) -> None:
         """Releases the peer-memory exchanges (every rank, after its last search has completed)."""
+        self.flush()
         for ex in self._p2p.values():
             if ex is not None:
                 ex.close()
@@ -286,6 +306,7 @@ class ShardedFlatIPIndex:
             # Bounded: a server with many batch shapes must not keep one IPC buffer set per shape for ever.  Every
             # rank sees the same sequence of shapes, so evicting the least recently used one is collective-safe.
             while len(self._p2p) >= self.MAX_P2P_SHAPES:
+                self.flush()          # no batch may still be using the exchange that is about to be closed
                 old_key = next(iter(self._p2p))
                 old = self._p2p.pop(old_key)
                 if old is not None:
@@ -353,20 +374,36 @@ class ShardedFlatIPIndex:
             self.local.search_shard_into(q, k_local, scores, ids, bound, flags)
 
     def search_async(self, q: torch.Tensor, k: int):
-        """Enqueues the whole sharded search (local search, all-gather, merge) and returns a PendingSearch;
-        `.result()` looks at the global certificate later (no host sync between consecutive batches)."""
+        """Enqueues the sharded search of one batch and returns a PendingSearch; `.result()` looks at the global
+        certificate later (no host sync between consecutive batches).
+
+        With the peer-memory exchange and the one-threshold plan the batches run as a 3-stage software pipeline on the
+        caller's stream, so that no rank ever idles in a wait kernel for a slower peer:
+            call j :  A(j)   sample pass of batch j, push of its top-r lists
+                      B(j-1) wait for the peers' lists of j-1, threshold, main scan, finalize, push of the record
+                      C(j-2) wait for the peers' records of j-2, merge + global certificate
+        `.result()` of a batch first enqueues whatever stages it (and every older batch) still misses.  Every rank
+        issues the same calls in the same order, so the exchanges pair up.  A caller that keeps three batches in
+        flight gets the full overlap; with fewer the stages simply run back to back."""
         from .vector_db import PendingSearch
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         nq = q.shape[0]
         self._validate(world, q.device)
         lay, rec, gathered = self._buffers(nq, k, q.device, world)
+        k_local = min(k, self.local.ntotal)
+        p2p = self._p2p_for(nq, k, q.device, world, lay)
+        n_local_min = self._n_local_min if self._n_local_min is not None else self.local.ntotal
+        plan_ok = getattr(self.local, "shard_plan_ok", None)
+        global_thr = (world > 1 and n_local_min >= k and plan_ok is not None
+                      and plan_ok(self.n_total, nq, k, max(n_local_min, 0)))
+        if p2p is not None and global_thr and self.pipelined:
+            return self._search_pipelined(q, k, nq, world, lay, rec, p2p)
+        self.flush()          # never interleave the two schedules
         views = record_views(rec, lay, nq, k)
         scores, ids, bound, flags = views
-        k_local = min(k, self.local.ntotal)
         if k_local < k:   # shard smaller than k: pad so every rank contributes [nq,k]
             scores.fill_(float("-inf"))
             ids.fill_(-1)
-        p2p = self._p2p_for(nq, k, q.device, world, lay)
         if p2p is not None:
             status = self._bufs.setdefault(("status", nq, k, world), torch.zeros(2, dtype=torch.int32, device=q.device))
             self._local_search(q, k, k_local, world, views, p2p, status)
@@ -379,25 +416,82 @@ class ShardedFlatIPIndex:
             s, i, fl, n_unc = self._merge(gathered, lay, nq, k)
         post = getattr(self.local, "post_flag", None)
         token = post(n_unc) if post is not None else None
+        return PendingSearch(lambda: self._finish(q, k, s, i, fl, n_unc, token))
 
-        def finish():
-            # identical on every rank: all ranks merged the same records
-            st = self.local.read_flag(token) if token is not None else int(n_unc)
-            if isinstance(st, list):
-                if st[1]:
-                    raise RuntimeError(f"sharded search: peer exchange {st[1]} timed out (a rank is missing)")
-                st = st[0]
-            n_bad = st
-            if not n_bad:
-                return s, i, 0
-            # Re-run the flagged queries alone (this rank's record buffer may already hold a later batch):
-            # exact fp32 search of every shard, a small exchange, merge, scatter into the result.
-            rows = torch.nonzero(fl != 1).flatten()
-            s2, i2 = self.search_exact_device(q[rows].contiguous(), k)
-            s[rows] = s2
-            i[rows] = i2
-            return s, i, n_bad
-        return PendingSearch(finish)
+    def _finish(self, q, k, s, i, fl, n_unc, token):
+        # identical on every rank: all ranks merged the same records
+        st = self.local.read_flag(token) if token is not None else int(n_unc)
+        if isinstance(st, list):
+            if st[1]:
+                raise RuntimeError(f"sharded search: peer exchange {st[1]} timed out (a rank is missing)")
+            st = st[0]
+        n_bad = st
+        if not n_bad:
+            return s, i, 0
+        # Re-run the flagged queries alone (this rank's record buffer may already hold a later batch):
+        # exact fp32 search of every shard, a small exchange, merge, scatter into the result.
+        rows = torch.nonzero(fl != 1).flatten()
+        s2, i2 = self.search_exact_device(q[rows].contiguous(), k)
+        s[rows] = s2
+        i[rows] = i2
+        return s, i, n_bad
+
+    # -- 3-stage pipeline -----------------------------------------------------------------------------------------
+    NSLOT = 3      # batches in flight: workspaces / status words are per slot
+
+    def _search_pipelined(self, q, k, nq, world, lay, rec, p2p):
+        from ._native import TT_SHARD_TOPR
+        from .vector_db import PendingSearch
+        self._pipe_seq = getattr(self, "_pipe_seq", 0) + 1
+        slot = self._pipe_seq % self.NSLOT
+        dev = q.device
+        topr = self._bufs.setdefault(("topr1", nq, world), torch.empty((nq, TT_SHARD_TOPR), device=dev, dtype=torch.float32))
+        status = self._bufs.setdefault(("status", nq, k, world, slot), torch.zeros(2, dtype=torch.int32, device=dev))
+        b = {"q": q, "k": k, "nq": nq, "world": world, "lay": lay, "rec": rec, "p2p": p2p, "slot": slot, "status": status,
+             "stage": 0, "out": None}
+        # stage A: sample pass + push of the top-r lists (no wait)
+        self.local.shard_sample(q, k, self.n_total, topr, slot)
+        b["seq0"] = p2p.push(0, topr.view(torch.uint8).view(-1))
+        b["stage"] = 1
+        self._inflight.append(b)
+        # advance the older batches by one stage each, oldest first
+        if len(self._inflight) >= 3:
+            self._advance(self._inflight[-3], 3)
+        if len(self._inflight) >= 2:
+            self._advance(self._inflight[-2], 2)
+        return PendingSearch(lambda: self._finish_pipelined(b))
+
+    def _advance(self, b, to_stage: int) -> None:
+        from ._native import TT_SHARD_TOPR
+        p2p, nq, k, world, lay = b["p2p"], b["nq"], b["k"], b["world"], b["lay"]
+        if b["stage"] < 2 <= to_stage:          # stage B
+            topr_g = p2p.wait(0, b["seq0"], b["status"]).view(torch.float32).view(world, nq, TT_SHARD_TOPR)
+            scores, ids, bound, flags = record_views(b["rec"], lay, nq, k)
+            self.local.shard_search_into(nq, k, self.n_total, topr_g, scores, ids, bound, flags, b["slot"])
+            b["seq1"] = p2p.push(1, b["rec"])
+            b["stage"] = 2
+        if b["stage"] < 3 <= to_stage:          # stage C
+            gathered = p2p.wait(1, b["seq1"], b["status"])
+            s, i, fl, _ = self._merge(gathered, lay, nq, k, b["status"][0:1])
+            post = getattr(self.local, "post_flag", None)
+            b["out"] = (s, i, fl, post(b["status"]) if post is not None else None)
+            b["stage"] = 3
+
+    def flush(self) -> None:
+        """Enqueues every stage still missing of every batch in flight (oldest first)."""
+        for b in list(self._inflight):
+            self._advance(b, 3)
+        self._inflight = [b for b in self._inflight if b["stage"] < 3]
+
+    def _finish_pipelined(self, b):
+        if b["stage"] < 3:
+            for older in list(self._inflight):
+                self._advance(older, 3)
+                if older is b:
+                    break
+        self._inflight = [x for x in self._inflight if x["stage"] < 3]
+        s, i, fl, token = b["out"]
+        return self._finish(b["q"], b["k"], s, i, fl, b["status"], token)
 
     def search_exact_device(self, q: torch.Tensor, k: int):
         """Always-exact fp32 path over the sharded catalog (collective: every rank calls it with the same q):

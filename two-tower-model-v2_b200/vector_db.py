@@ -424,31 +424,33 @@ class FlatIPIndex:
     def shard_plan_ok(self, n_total: int, nq: int, k: int, n_local_min: int) -> bool:
         return bool(_native.load().tt_flat_shard_plan_ok(int(n_local_min), int(n_total), self.d, int(nq), int(k)))
 
-    def _shard_workspace(self, n_total: int, nq: int, k: int) -> torch.Tensor:
-        key = ("shard", n_total, nq, k)
+    def _shard_workspace(self, n_total: int, nq: int, k: int, slot: int = 0) -> torch.Tensor:
+        key = ("shard", n_total, nq, k, slot)
         ws = self._ws.get(key)
         if ws is None:
             nbytes = int(_native.load().tt_flat_shard_workspace_bytes(self.ntotal, n_total, self.d, nq, k))
             ws = torch.empty(max(nbytes, 256), device=self.device, dtype=torch.uint8)
-            if len(self._ws) > 8:
+            if len(self._ws) > 12:
                 self._ws.clear()
             self._ws[key] = ws
         return ws
 
-    def shard_sample(self, q: torch.Tensor, k: int, n_total: int, topr: torch.Tensor) -> None:
-        """Phase 1 of the sharded search: fills topr f32 [nq, TT_SHARD_TOPR] (this shard's largest sampled scores)."""
+    def shard_sample(self, q: torch.Tensor, k: int, n_total: int, topr: torch.Tensor, slot: int = 0) -> None:
+        """Phase 1 of the sharded search: fills topr f32 [nq, TT_SHARD_TOPR] (this shard's largest sampled scores).
+        `slot` selects the workspace (phase 2 of the same batch must use the same slot; batches in flight at the same
+        time need different slots)."""
         q = ops._f32c(q, "queries")
-        ws = self._shard_workspace(n_total, q.shape[0], k)
+        ws = self._shard_workspace(n_total, q.shape[0], k, slot)
         with torch.cuda.device(self.device):
             _native.check(_native.load().tt_flat_shard_sample(
                 q.data_ptr(), q.shape[0], self.xh.data_ptr(), self.stats.data_ptr(), self.ntotal, n_total, self.d, k,
                 topr.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream()), "tt_flat_shard_sample")
 
     def shard_search_into(self, nq: int, k: int, n_total: int, topr_g: torch.Tensor, scores: torch.Tensor,
-                          ids: torch.Tensor, bound: torch.Tensor, flags: torch.Tensor) -> None:
+                          ids: torch.Tensor, bound: torch.Tensor, flags: torch.Tensor, slot: int = 0) -> None:
         """Phase 2: global threshold from the gathered lists [G, nq, TT_SHARD_TOPR], main scan, finalize into
         the record views (scores/ids must be contiguous [nq,k])."""
-        ws = self._shard_workspace(n_total, nq, k)
+        ws = self._shard_workspace(n_total, nq, k, slot)
         nunc = torch.empty((1,), device=self.device, dtype=torch.int32)
         with torch.cuda.device(self.device):
             _native.check(_native.load().tt_flat_shard_search(
