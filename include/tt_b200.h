@@ -110,7 +110,7 @@ int tt_pool_partial_merge(const float* partials_g, int G, int attention, float* 
 /* attention_aggregation in ONE kernel and one pass over x in HBM (buyer_tower.py:70-101): the score MLP runs on
  * the tensor cores (fp16 two-piece split of both operands, fp32 accumulation in TMEM: fp32-accurate) while the rows
  * stream in through TMA, and the softmax-weighted row sum + L2 normalisation re-read the rows while they are still in
- * L2.  Fused for D % 64 == 0, D <= 384, H <= 128, S <= 8192, B*S >= 4096; any other shape runs tt_attention_logits +
+ * L2.  Fused for D % 64 == 0, D <= 384, H <= 128, S <= 8192, B*S >= 64; any other shape runs tt_attention_logits +
  * tt_pool_attention behind the same entry point.  Inputs outside the fp16 range after scaling (|x| > 4094, inf, nan)
  * are detected on the device and recomputed by a predicated fp32 CUDA-core kernel (no host synchronisation).
  * workspace: tt_pool_attention_fused_workspace_bytes(B,S,D,H) bytes of device memory, 256-byte aligned. */

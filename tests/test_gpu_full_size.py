@@ -128,3 +128,22 @@ def test_sharded_on_real_gpus_equals_single_index(N, D, nq):
                        capture_output=True, text=True, cwd=root, timeout=900)
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
     assert "sharded==single ids True scores True" in r.stdout and "vs fp32 exact path (16 queries) True" in r.stdout
+
+
+def test_sharded_retrieve_path_on_real_gpus_equals_single_device():
+    """BASELINE config C5 shape on real GPUs (skipped on a 1-GPU box): owner-computes pooling over the row-sharded item
+    table + sharded exact top-K == the single-device /retrieve pipeline (tools/check_sharded_retrieve.py)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    G = torch.cuda.device_count()
+    if G < 2:
+        pytest.skip("needs >= 2 GPUs")
+    G = 8 if G >= 8 else (4 if G >= 4 else 2)
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(G),
+                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+                        str(root / "tools" / "check_sharded_retrieve.py"), "4000000", "384", "256", "50", str(K)],
+                       capture_output=True, text=True, cwd=root, timeout=900)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert r.stdout.count("ok=True") >= 4

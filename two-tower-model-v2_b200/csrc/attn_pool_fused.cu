@@ -25,14 +25,14 @@
 //
 // Persistent CTAs (one per SM, 20 warps); CTA c owns a contiguous range of buyers and walks its rows in 64-row tiles:
 //   warp 0 lane 0   : TMA producer  - raw fp32 [64 rows x 64 cols] (two 128B-swizzled boxes) per K-block, 6-stage ring
-//   warps 8-15      : splitters     - raw fp32 -> scaled fp16 hi/lo tiles in the UMMA K-major 128B-swizzle layout
+//   warps 8-11      : splitters     - raw fp32 -> scaled fp16 hi/lo tiles in the UMMA K-major 128B-swizzle layout
 //                                     (3-stage ring), fence.proxy.async, arrive
 //   warp 1 lane 0   : MMA issuer    - per K-block 4 K-steps x 3 MMAs (M = 128 hidden, N = 64 rows, K = 16) into the main
 //                                     and the cross-term accumulator (2 x 64 TMEM columns; the kernel is HBM-bound, the
 //                                     tensor pipe may idle while the epilogue reads them)
 //   warps 4-7       : epilogue      - lane = hidden unit: relu(acc*2^-e + b1)*W2, butterfly transpose-reduce over
 //                                     the 128 hidden units -> one logit per row into a shared-memory array
-//   warps 16-19     : pooling       - one warp per buyer, as soon as the tile holding the buyer's last row is done:
+//   warps 12-19     : pooling       - one warp per buyer, as soon as the tile holding the buyer's last row is done:
 //                                     softmax of logit*weight, weighted row sum (128-bit loads, L2 hits), L2 normalise
 //   warp 2          : TMEM allocator
 // Rooflines: HBM (x once: B*S*D*4 bytes); tensor pipe 3 x 2*D*128 flop per row at the fp16 rate; shared memory
@@ -56,8 +56,9 @@ constexpr int AF_RAW_STAGES = 6;
 constexpr int AF_B_STAGES = 3;
 constexpr int AF_RMAX = 8192;                        // rows (logits) one CTA may own per launch
 constexpr int AF_MAX_KB = 6;                         // D <= 384: W hi + lo = 2 * 6 * 32 = 384 TMEM columns
-constexpr int AF_SPLIT_WARPS = 8;
-constexpr int AF_POOL_WARPS = 4;
+constexpr int AF_SPLIT_WARPS = 4;
+constexpr int AF_POOL_WARPS = 8;                     // the re-read must keep pace with the stream or it falls out of L2
+constexpr int AF_POOL_WARP0 = 8 + AF_SPLIT_WARPS;
 constexpr int AF_WARPS = 20;
 constexpr int AF_THREADS = AF_WARPS * 32;
 constexpr int AF_ACC_COLS = 128;                     // main + cross-term accumulator (64 columns each), then W hi, W lo
@@ -288,7 +289,7 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
     }
   } else if (warp >= 8 && warp < 8 + AF_SPLIT_WARPS) {
     // =========================== splitters ==========================================================
-    const int tid = (warp - 8) * 32 + lane;                    // 0..255
+    const int tid = (warp - 8) * 32 + lane;                    // 0..127
     int rstage = 0, bstage = 0;
     uint32_t rphase = 0, bphase = 0;
     float mabs = 0.f;
@@ -296,11 +297,12 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
     for (int n = 0; n < nsteps; ++n) {
       mbar_wait(smem_u32(full_raw + rstage), rphase, 550 + rstage);
       const uint8_t* raw = raw_ring + (size_t)rstage * AF_RAW_STAGE;
-      float4 fa[2], fb[2];
-      int row[2], cpos[2];
+      constexpr int UPT = 512 / (AF_SPLIT_WARPS * 32);           // 32-byte units per thread per stage
+      float4 fa[UPT], fb[UPT];
+      int row[UPT], cpos[UPT];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int u = tid + 256 * i;
+      for (int i = 0; i < UPT; ++i) {
+        const int u = tid + AF_SPLIT_WARPS * 32 * i;
         row[i] = u >> 3;
         const int sub = u & 7, box = sub >> 2, j = sub & 3;
         const int x7 = row[i] & 7;
@@ -320,7 +322,7 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
       uint8_t* hi_tile = b_ring + (size_t)bstage * AF_B_STAGE;
       uint8_t* lo_tile = hi_tile + AF_B_STAGE / 2;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < UPT; ++i) {
         uint4 hi, lo;
         split8(fa[i], fb[i], hi, lo, mabs);
         *reinterpret_cast<uint4*>(hi_tile + row[i] * 128 + cpos[i]) = hi;
@@ -332,9 +334,9 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
       if (++bstage == AF_B_STAGES) { bstage = 0; bphase ^= 1; }
     }
     if (!(mabs <= AF_F16_MAX)) atomicOr(p.flag, 1);
-  } else if (POOL && warp >= 16) {
+  } else if (POOL && warp >= AF_POOL_WARP0) {
     // =========================== pooling: one warp per buyer ==========================================
-    const int pw = warp - 16;
+    const int pw = warp - AF_POOL_WARP0;
     const int S = p.S, D = p.D;
     const int nvalid4 = D >> 2;
     constexpr int NV = 3, U = 4;
@@ -548,7 +550,7 @@ static FusedWs fused_ws_layout(int nkb) {
 }
 
 static bool fused_shape_ok(const float* x, const float* out, long long B, long long S, int D, int H) {
-  return D % 64 == 0 && D <= 64 * AF_MAX_KB && H >= 1 && H <= AF_M && S >= 1 && S <= AF_RMAX && B * S >= 4096 &&
+  return D % 64 == 0 && D <= 64 * AF_MAX_KB && H >= 1 && H <= AF_M && S >= 1 && S <= AF_RMAX && B * S >= 64 &&
          B * S < (1LL << 31) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 }
 
