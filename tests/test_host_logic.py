@@ -157,12 +157,9 @@ def test_search_planner_invariants():
                         (10_000_000, 384, 129, 100), (10_000_000, 768, 300, 100)]:
         p = _plan(N, D, nq, K)
         assert p["supported"] == 1 and p["smem"] <= 227 * 1024 and p["stages"] >= 2
-        # nq > 256: queries in tensor memory (flat_scan_ts.cu), 2 blocks of 256 per CTA pair when both fit the 512
-        # TMEM columns next to the accumulators (D <= 384), else 1 (D <= 768); 64-row catalog tiles.
-        # 128 < nq <= 256: CTA pairs with the query block in shared memory (rows wider than 640 stream part of it);
-        # single CTAs keep 128 resident queries while >= 3 full stages fit (D <= 512), else 64
-        ts = nq > 256 and D <= 768
-        want = (512 if D <= 384 else 256) if ts else (256 if nq > 128 else (64 if D > 512 else 128))
+        # CTA pairs (256 queries per unit) exactly when nq > 128 (rows wider than 640 stream part of the query
+        # block); single CTAs keep 128 resident queries while >= 3 full stages fit (D <= 512), else 64
+        want = 256 if nq > 128 else (64 if D > 512 else 128)
         assert p["unit_queries"] == want
         assert p["k_blocks"] == -(-D // 64) and p["tiles"] == -(-N // 256)
         assert p["query_units"] == -(-nq // want)
@@ -180,10 +177,7 @@ def test_search_planner_invariants():
     # units fill the machine: one unit per SM (single) / SM pair (pair) on a 148-SM part
     assert _plan(10_000_000, 384, 128, 100)["main_slices"] == 148
     assert _plan(10_000_000, 384, 256, 100)["main_slices"] == 74
-    # nq = 4096 at D = 384: 8 units of 512 queries x 9 slices = 72 of the 74 SM pairs, one wave
-    p = _plan(10_000_000, 384, 4096, 100)
-    assert (p["unit_queries"], p["query_units"], p["main_slices"]) == (512, 8, 9)
-    assert _plan(10_000_000, 768, 4096, 100)["unit_queries"] == 256
+
 
 
 def test_retrieval_pipeline_history_encoding():
@@ -266,9 +260,8 @@ def test_search_planner_properties_random_shapes():
             assert D > 512                                   # only very wide rows may be rejected
             return
         assert p["smem"] <= 227 * 1024 and p["stages"] >= 2 and p["stages"] <= 8
-        assert p["unit_queries"] in (64, 128, 256, 512)
-        assert (p["unit_queries"] >= 256) == (nq > 128)
-        assert (p["unit_queries"] == 512) == (nq > 256 and D <= 384)
+        assert p["unit_queries"] in (64, 128, 256)
+        assert (p["unit_queries"] == 256) == (nq > 128)
         assert p["query_units"] * p["unit_queries"] >= nq
         assert 1 <= p["main_slices"] <= max(p["tiles"], 1) and p["main_slices"] <= 1024
         ws = lib.tt_flat_search_workspace_bytes(N, D, nq, K)

@@ -225,7 +225,7 @@ extern "C" __attribute__((visibility("default"))) size_t tt_flat_scan_scores_wor
   ScanPlan pl = make_scan_plan(N, D, nq, 1);
   pl.use_threshold = false;
   pl.route_exact = false;
-  pl.seg_cap = pl.ts ? (pl.ts_tiles + pl.main_slices - 1) / pl.main_slices * 64 : (pl.num_tiles + pl.main_slices - 1) / pl.main_slices * 256;
+  pl.seg_cap = (pl.num_tiles + pl.main_slices - 1) / pl.main_slices * 256;
   return search_ws_layout(pl, D, nq).total;
 }
 
@@ -238,7 +238,7 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_scan_scores(const 
   if (!pl.supported) { set_error("tt_flat_scan_scores: D too large"); return TT_ERR_UNSUPPORTED; }
   pl.use_threshold = false;
   pl.route_exact = false;
-  pl.seg_cap = pl.ts ? (pl.ts_tiles + pl.main_slices - 1) / pl.main_slices * 64 : (pl.num_tiles + pl.main_slices - 1) / pl.main_slices * 256;
+  pl.seg_cap = (pl.num_tiles + pl.main_slices - 1) / pl.main_slices * 256;
   const SearchWs w = search_ws_layout(pl, D, nq);
   if (workspace_bytes < w.total) { set_error("tt_flat_scan_scores: workspace too small"); return TT_ERR_WORKSPACE; }
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
@@ -261,8 +261,7 @@ extern "C" __attribute__((visibility("default"))) int tt_flat_scan_scores(const 
 extern "C" __attribute__((visibility("default"))) int tt_flat_plan_describe(int64_t N, int D, int nq, int K, int32_t* out16) {
   TT_CHECK_ARG(out16 != nullptr && N >= 1 && D >= 1 && nq >= 1 && K >= 1, "bad argument");
   const ScanPlan pl = make_scan_plan(N, D, nq, K);
-  const int32_t v[16] = {pl.supported, pl.ts ? 256 * pl.ts_nqb : (pl.pair ? 2 * pl.block_m : pl.block_m), pl.num_kb,
-                         pl.ts ? pl.ts_slots : pl.num_stages, pl.ts ? pl.ts_nqu : pl.nqu, pl.num_tiles,
+  const int32_t v[16] = {pl.supported, pl.pair ? 2 * pl.block_m : pl.block_m, pl.num_kb, pl.num_stages, pl.nqu, pl.num_tiles,
                          pl.use_threshold, pl.route_exact, pl.target, pl.cand_cap, pl.sample_stride, pl.sample_slots,
                          pl.sample_rank, pl.main_slices, pl.seg_cap, (int32_t)pl.smem_bytes};
   for (int i = 0; i < 16; ++i) out16[i] = v[i];

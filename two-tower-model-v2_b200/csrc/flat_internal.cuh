@@ -28,10 +28,6 @@ struct ScanPlan {
   int main_slices;
   int sample_stride, sample_slots, sample_slices, sample_rank;
   bool sample_tile_max;  // sample pass records one maximum per sampled tile (else one per 32-row chunk)
-  // main scan with the queries in tensor memory (flat_scan_ts.cu; nq > 256): NQB blocks of 256 queries per CTA
-  // pair, 64-row catalog tiles, a ring of whole tiles in shared memory
-  bool ts;
-  int ts_nqb, ts_nqu, ts_tiles, ts_slots;
 };
 
 ScanPlan make_scan_plan(long long N, int D, int nq, int K);
@@ -51,8 +47,6 @@ int launch_sample(const ScanPlan& pl, const void* qh, const void* Xh, long long 
 int launch_select_gathered(const float* topr_g, int G, int nq, int r, float* thr, int* zero_me, cudaStream_t st);
 int launch_main_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr,
                      unsigned int* seg_cnt, void* cand, cudaStream_t st);
-int launch_main_scan_ts(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr,
-                        unsigned int* seg_cnt, void* cand, cudaStream_t st);
 
 // fp32 rescoring of every candidate, exact sort, certificate
 int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long long N, int D, int nq, int K,

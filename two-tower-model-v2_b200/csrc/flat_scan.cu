@@ -529,10 +529,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // bf16 [rows, pitch] row-major, box = [box_rows, 64 columns], 128-byte swizzle, OOB rows read as 0.
 static int encode_tmap_bf16(CUtensorMap* m, const void* base, long long rows, int pitch, int box_rows);
-static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, int pitch, int box_rows);
-int make_tmap_bf16(void* tensor_map, const void* base, long long rows, int pitch, int box_rows) {
-  return make_tmap_bf16(reinterpret_cast<CUtensorMap*>(tensor_map), base, rows, pitch, box_rows);
-}
+
 
 // A search call encodes four descriptors (query block + catalog, sample + main pass) that only depend on
 // (base, rows, pitch, box): a small per-thread cache saves the driver calls on the small-batch path, where the
@@ -652,29 +649,6 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   pl.num_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
   const int cap_units = pl.pair ? sms / 2 : sms;
   pl.main_slices = pick_slices(pl.nqu, cap_units, pl.num_tiles);
-  // Large batches: queries in tensor memory (flat_scan_ts.cu).  2 blocks of 256 queries per CTA pair when both fit
-  // next to the two 64-column accumulator slots (Dp <= 384), else 1 (Dp <= 768).
-  pl.ts = false;
-  static const bool ts_on = [] { const char* e = getenv("TT_B200_SCAN_TS"); return !(e && e[0] == '0'); }();
-  if (pl.pair && pl.supported && nq > 256 && ts_on) {
-    const int qcols = pl.Dp / 2;
-    const int nqb2 = (2 * qcols + 128 <= TMEM_COLS) ? 2 : ((qcols + 128 <= TMEM_COLS) ? 1 : 0);
-    if (nqb2 > 0) {
-      pl.ts = true;
-      pl.ts_nqb = nqb2;
-      const int unit_q = 256 * nqb2;
-      pl.nq_pad = (nq + unit_q - 1) / unit_q * unit_q;
-      pl.nqb = pl.nq_pad / pl.block_m;
-      pl.nqu = pl.nqb / 2;                                   // the sample pass still runs 256-query pairs
-      pl.ts_nqu = pl.nq_pad / unit_q;
-      pl.ts_tiles = (int)((N + 63) / 64);
-      const int slot_bytes = pl.num_kb * 32 * 128;          // this CTA's half of a 64-row tile
-      pl.ts_slots = (budget) / slot_bytes;
-      if (pl.ts_slots > 8) pl.ts_slots = 8;
-      if (pl.ts_slots < 2) pl.ts = false;
-      else pl.main_slices = pick_slices(pl.ts_nqu, cap_units, pl.num_tiles);     // never more slices than 256-row tiles
-    }
-  }
 
   // Candidate budget and sampling plan.  We aim at ~T candidates per query: the threshold is read
   // among the 32-row chunk maxima of every `stride`-th tile at the rank r' = T * n_s / N (n_s =
@@ -734,8 +708,7 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   // if the catalog fits a candidate list, else the always-exact fp32 path.
   pl.route_exact = false;
   pl.use_threshold = reliable;
-  const long long slice_rows = pl.ts ? ((long long)(pl.ts_tiles + pl.main_slices - 1) / pl.main_slices) * 64
-                                     : ((long long)(pl.num_tiles + pl.main_slices - 1) / pl.main_slices) * BLOCK_N;
+  const long long slice_rows = ((long long)(pl.num_tiles + pl.main_slices - 1) / pl.main_slices) * BLOCK_N;
   if (!reliable) {
     pl.sample_stride = 1; pl.sample_slots = 1; pl.sample_rank = 1; pl.target = 0; pl.sample_tile_max = false;
     if (N <= FINALIZE_MAX_CAND) {
@@ -856,7 +829,6 @@ int launch_select_gathered(const float* topr_g, int G, int nq, int r, float* thr
 
 int launch_main_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr,
                      unsigned int* seg_cnt, void* cand, cudaStream_t st) {
-  if (pl.ts) return launch_main_scan_ts(pl, qh, Xh, N, nq, thr, seg_cnt, cand, st);
   CUtensorMap tq, tx;
   ScanParams sp;
   if (int e = make_scan_params(pl, qh, Xh, N, nq, thr, seg_cnt, cand, nullptr, &tq, &tx, &sp)) return e;
@@ -898,8 +870,7 @@ ScanPlan make_shard_plan(long long N_local, long long N_total, int D, int nq, in
   const int cap_units = pl.pair ? num_sms() / 2 : num_sms();
   pl.sample_slices = pick_slices(pl.nqu, cap_units, pl.sample_slots);
   // a shard may hold every candidate of a query (clustered catalogs): size its segments for the whole target
-  const long long slice_rows = pl.ts ? ((long long)(pl.ts_tiles + pl.main_slices - 1) / pl.main_slices) * 64
-                                     : ((long long)(pl.num_tiles + pl.main_slices - 1) / pl.main_slices) * BLOCK_N;
+  const long long slice_rows = ((long long)(pl.num_tiles + pl.main_slices - 1) / pl.main_slices) * BLOCK_N;
   long long seg = 4LL * pl.target / pl.main_slices;
   if (seg < 512) seg = 512;
   if (seg > pl.cand_cap) seg = pl.cand_cap;

@@ -193,17 +193,6 @@ __device__ __forceinline__ void mma_bf16_ss_2cta(uint32_t tmem_d, uint64_t desc_
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// CTA-pair MMA with the A operand in tensor memory: each CTA's TMEM holds its own 128 rows of A (one per lane,
-// K bf16 elements packed two per 32-bit column) at the same column address; B as for mma_bf16_ss_2cta.
-__device__ __forceinline__ void mma_bf16_ts_2cta(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                                 uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // Arrive on the barrier at this offset in BOTH CTAs of the pair once the issued MMAs have completed.
 __device__ __forceinline__ void mma_commit_2cta(uint32_t bar) {
   const uint16_t mask = 3;
