@@ -150,23 +150,38 @@ __global__ void __launch_bounds__(128)
 attn_logits_generic_kernel(const float* __restrict__ x, long long R, int D,
                            const float* __restrict__ W1, const float* __restrict__ b1,
                            const float* __restrict__ W2, const float* __restrict__ b2, int H,
-                           float* __restrict__ logits) {
+                           float* __restrict__ logits, const int* __restrict__ run_if) {
+  pdl_wait();
+  if (run_if && *run_if == 0) return;       // predicated fp32 recomputation behind the tensor-core kernel
   extern __shared__ float xs[];
   __shared__ float red[4];
-  const long long r = blockIdx.x;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = x[r * D + d];
-  __syncthreads();
-  float part = 0.f;
-  for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    float a = 0.f;
-    const float* wr = W1 + (long long)h * D;
-    for (int d = 0; d < D; ++d) a = fmaf(xs[d], __ldg(wr + d), a);
-    part = fmaf(fmaxf(a + __ldg(b1 + h), 0.f), __ldg(W2 + h), part);
+  for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = x[r * D + d];
+    __syncthreads();
+    float part = 0.f;
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+      float a = 0.f;
+      const float* wr = W1 + (long long)h * D;
+      for (int d = 0; d < D; ++d) a = fmaf(xs[d], __ldg(wr + d), a);
+      part = fmaf(fmaxf(a + __ldg(b1 + h), 0.f), __ldg(W2 + h), part);
+    }
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) logits[r] = red[0] + red[1] + red[2] + red[3] + __ldg(b2);
+    __syncthreads();
   }
-  part = warp_sum(part);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
-  __syncthreads();
-  if (threadIdx.x == 0) logits[r] = red[0] + red[1] + red[2] + red[3] + __ldg(b2);
+}
+
+// predicated launch for attn_pool_fused.cu (logits-only mode): recompute every row in fp32 when *run_if != 0
+int launch_attn_logits_generic_if(const float* x, long long R, int D, const float* W1, const float* b1, const float* W2,
+                                  const float* b2, int H, float* logits, const int* run_if, cudaStream_t st) {
+  TT_CHECK_ARG(R <= 0x7fffffffLL && (size_t)D * sizeof(float) <= 48 * 1024, "shape too large for the generic logits kernel");
+  count_launch();
+  const long long cap = (long long)num_sms() * 16;       // grid-stride: an all-exit launch stays a few microseconds
+  TT_CHECK_CUDA(launch_pdl(attn_logits_generic_kernel, dim3((unsigned)(R < cap ? R : cap)), dim3(128), (size_t)D * sizeof(float),
+                           st, x, R, D, W1, b1, W2, b2, H, logits, run_if));
+  return TT_OK;
 }
 
 }  // namespace tt
@@ -185,9 +200,14 @@ extern "C" __attribute__((visibility("default"))) int tt_attention_logits(const 
   // Tensor-core path (3xTF32, fp32-accurate) for aligned shapes with H <= 256; TT_B200_ATTN_LOGITS=fma keeps the
   // CUDA-core FFMA2 kernel.
   static const bool want_tc = [] { const char* e = getenv("TT_B200_ATTN_LOGITS"); return !(e && strcmp(e, "fma") == 0); }();
-  if (fast && want_tc && R >= 128) {
-    const int e = launch_attn_logits_tc(x, R, D, W1, b1, W2, b2, H, logits, st);
+  if (fast && want_tc && R >= 64 && R < (1LL << 31)) {
+    // D % 64 == 0, D <= 384, H <= 128: the fp16 two-piece kernel of the fused pooling in its logits-only mode
+    int e = launch_attn_logits_fused(x, R, D, W1, b1, W2, b2, H, logits, st);
     if (e != TT_ERR_UNSUPPORTED) return e;
+    if (R >= 128) {
+      e = launch_attn_logits_tc(x, R, D, W1, b1, W2, b2, H, logits, st);
+      if (e != TT_ERR_UNSUPPORTED) return e;
+    }
   }
   if (fast) {
     const size_t smem = 2 * AL_STAGE_FLOATS * sizeof(float);
@@ -198,7 +218,7 @@ extern "C" __attribute__((visibility("default"))) int tt_attention_logits(const 
   } else {
     TT_CHECK_ARG(R <= 0x7fffffffLL, "too many rows");
     TT_CHECK_ARG((size_t)D * sizeof(float) <= 48 * 1024, "D too large for the generic logits kernel");
-    attn_logits_generic_kernel<<<(unsigned)R, 128, (size_t)D * sizeof(float), st>>>(x, R, D, W1, b1, W2, b2, H, logits);
+    attn_logits_generic_kernel<<<(unsigned)R, 128, (size_t)D * sizeof(float), st>>>(x, R, D, W1, b1, W2, b2, H, logits, nullptr);
   }
   TT_CHECK_LAUNCH();
   return TT_OK;

@@ -251,7 +251,7 @@ __global__ void attn_split_w_kernel(const float* __restrict__ W1, int H, int Hp,
 
 // Library-private stream-ordered memory pool (one per device) for the split weights: blocks are reused across
 // calls instead of going back to the driver at every synchronisation (the default pool's behaviour).
-static cudaMemPool_t scratch_pool(int dev) {
+cudaMemPool_t scratch_pool(int dev) {
   static std::mutex mu;
   static cudaMemPool_t pools[64] = {};
   std::lock_guard<std::mutex> lock(mu);

@@ -216,6 +216,7 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
     const int e = warp - 4;                      // TMEM lane quadrant
     const int h = e * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(e * 32) << 16);
+    pdl_wait();      // the weight-preparation kernel (previous launch) has written Wp / inv_scale / flag
     // one-time: this CTA's copy of the W1 pieces into tensor memory (A operand of every MMA)
     for (int j = 0; j < 2 * nkb; ++j) {
       const uint4* src = p.Wp + (size_t)j * 8 * AF_M + h;
@@ -333,6 +334,7 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
       if (lane == 0) mbar_arrive(smem_u32(full_b + bstage));
       if (++bstage == AF_B_STAGES) { bstage = 0; bphase ^= 1; }
     }
+    pdl_wait();      // ... and cleared the flag
     if (!(mabs <= AF_F16_MAX)) atomicOr(p.flag, 1);
   } else if (POOL && warp >= AF_POOL_WARP0) {
     // =========================== pooling: one warp per buyer ==========================================
@@ -489,13 +491,15 @@ attn_fused_prep_w_kernel(const float* __restrict__ W1, int H, int D, int nkb, ui
 __global__ void __launch_bounds__(256)
 attn_pool_fallback_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ W1,
                           const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
-                          int H, float* __restrict__ out, int S, int D, const int* __restrict__ flag) {
+                          int H, float* __restrict__ out, int B, int S, int D, const int* __restrict__ flag) {
+  pdl_wait();
   if (*flag == 0) return;
   extern __shared__ float fsm[];
   float* lg = fsm;                 // [S]
   float* hsum = fsm + S;           // [8] per-warp partial logits
   __shared__ float bc[2];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
   const float* xb = x + (long long)b * S * D;
   for (int s = 0; s < S; ++s) {
     const float* row = xb + (long long)s * D;
@@ -538,6 +542,8 @@ attn_pool_fallback_kernel(const float* __restrict__ x, const float* __restrict__
   __syncthreads();
   const float denom = bc[0];
   for (int d = tid; d < D; d += blockDim.x) out[(long long)b * D + d] /= denom;
+  __syncthreads();
+  }
 }
 
 struct FusedWs { size_t wp, meta, total; };
@@ -552,6 +558,46 @@ static FusedWs fused_ws_layout(int nkb) {
 static bool fused_shape_ok(const float* x, const float* out, long long B, long long S, int D, int H) {
   return D % 64 == 0 && D <= 64 * AF_MAX_KB && H >= 1 && H <= AF_M && S >= 1 && S <= AF_RMAX && B * S >= 64 &&
          B * S < (1LL << 31) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+}
+
+// Logits-only mode (tt_attention_logits; e.g. once over the whole catalog for the gather path): the same kernel without
+// the pooling warps, logits written to global memory; the weight pieces live in a stream-ordered scratch block.
+int launch_attn_logits_fused(const float* x, long long R, int D, const float* W1, const float* b1, const float* W2,
+                             const float* b2, int H, float* logits, cudaStream_t st) {
+  if (!(D % 64 == 0 && D <= 64 * AF_MAX_KB && H >= 1 && H <= AF_M && R >= 64 && R < (1LL << 31) &&
+        (reinterpret_cast<uintptr_t>(x) & 15) == 0))
+    return TT_ERR_UNSUPPORTED;
+  int dev = 0;
+  TT_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool = scratch_pool(dev);
+  if (!pool) return TT_ERR_UNSUPPORTED;
+  const int nkb = D / 64;
+  const FusedWs lay = fused_ws_layout(nkb);
+  unsigned char* ws = nullptr;
+  TT_CHECK_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&ws), lay.total, pool, st));
+  uint4* Wp = reinterpret_cast<uint4*>(ws + lay.wp);
+  float* inv_scale = reinterpret_cast<float*>(ws + lay.meta);
+  int* flag = reinterpret_cast<int*>(ws + lay.meta + 16);
+  attn_fused_prep_w_kernel<<<(AF_M * nkb * 8 + AF_PREP_THREADS - 1) / AF_PREP_THREADS, AF_PREP_THREADS, 0, st>>>(W1, H, D, nkb, Wp, inv_scale, flag);
+  count_launch();
+  int rc = TT_OK;
+  CUtensorMap tx;
+  if ((rc = make_tmap_f32(&tx, x, R, D, AF_TILE, 32)) == TT_OK) {
+    AttnFusedParams p{};
+    p.x = x; p.logits_out = logits; p.Wp = Wp; p.b1 = b1; p.W2 = W2; p.b2 = b2; p.inv_scale = inv_scale; p.flag = flag;
+    p.R = R; p.B = (int)R; p.S = 1; p.D = D; p.H = H; p.nkb = nkb;
+    const size_t smem = (size_t)AF_RAW_STAGES * AF_RAW_STAGE + (size_t)AF_B_STAGES * AF_B_STAGE + AF_RMAX * sizeof(float) +
+                        2 * 4 * AF_TILE * sizeof(float) + 512 + 1024;
+    const long long tiles = (R + AF_TILE - 1) / AF_TILE;
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    cudaError_t ce = cudaFuncSetAttribute(attn_pool_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce == cudaSuccess) { count_launch(); ce = launch_pdl(attn_pool_fused_kernel<false>, dim3(grid), dim3(AF_THREADS), smem, st, tx, p); }
+    if (ce != cudaSuccess) { set_error(std::string("launch_attn_logits_fused: ") + cudaGetErrorString(ce)); rc = TT_ERR_CUDA; }
+    if (rc == TT_OK) rc = launch_attn_logits_generic_if(x, R, D, W1, b1, W2, b2, H, logits, flag, st);
+  }
+  const cudaError_t fe = cudaFreeAsync(ws, st);
+  if (rc == TT_OK && fe != cudaSuccess) { set_error("launch_attn_logits_fused: cudaFreeAsync failed"); rc = TT_ERR_CUDA; }
+  return rc;
 }
 
 }  // namespace tt
@@ -606,14 +652,19 @@ extern "C" __attribute__((visibility("default"))) int tt_pool_attention_fused(co
     p.b1 = b1; p.W2 = W2; p.b2 = b2; p.inv_scale = inv_scale; p.flag = flag;
     p.R = nb * S; p.B = (int)nb; p.S = S; p.D = D; p.H = H; p.nkb = nkb;
     const int grid = (int)(nb < sms ? nb : sms);
-    attn_pool_fused_kernel<true><<<grid, AF_THREADS, smem, st>>>(tx, p);
-    TT_CHECK_LAUNCH();
+    // programmatic dependent launch: the x stream (TMA, splitters) starts under the weight-preparation kernel's tail;
+    // only the epilogue warps (W1 pieces, scale) and the flag wait for it.  The preparation kernel itself is a plain
+    // launch, so everything that produced x has completed before either kernel starts.
+    count_launch();
+    TT_CHECK_CUDA(launch_pdl(attn_pool_fused_kernel<true>, dim3(grid), dim3(AF_THREADS), smem, st, tx, p));
     bdone += nb;
   }
   const size_t fsm = (size_t)(S + 8) * sizeof(float);
   if (fsm > 48 * 1024)
     TT_CHECK_CUDA(cudaFuncSetAttribute(attn_pool_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-  attn_pool_fallback_kernel<<<B, 256, fsm, st>>>(x, w, W1, b1, W2, b2, H, out, S, D, flag);
-  TT_CHECK_LAUNCH();
+  count_launch();
+  const int fgrid = B < num_sms() * 8 ? B : num_sms() * 8;      // grid-stride: an all-exit launch stays a few microseconds
+  TT_CHECK_CUDA(launch_pdl(attn_pool_fallback_kernel, dim3(fgrid), dim3(256), fsm, st, x, w, W1, b1, W2, b2, H, out, B, S, D,
+                           (const int*)flag));
   return TT_OK;
 }

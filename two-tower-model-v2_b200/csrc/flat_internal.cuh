@@ -59,6 +59,14 @@ int make_tmap_f32(void* tensor_map /* CUtensorMap* */, const void* base, long lo
 int launch_attn_logits_tc(const float* x, long long R, int D, const float* W1, const float* b1, const float* W2,
                           const float* b2, int H, float* logits, cudaStream_t st);
 
+// attn_pool_fused.cu in logits-only mode (TT_ERR_UNSUPPORTED without an error message when the shape does not fit),
+// its predicated fp32 recomputation (attn_logits.cu) and the library-private stream-ordered scratch pool
+int launch_attn_logits_fused(const float* x, long long R, int D, const float* W1, const float* b1, const float* W2,
+                             const float* b2, int H, float* logits, cudaStream_t st);
+int launch_attn_logits_generic_if(const float* x, long long R, int D, const float* W1, const float* b1, const float* W2,
+                                  const float* b2, int H, float* logits, const int* run_if, cudaStream_t st);
+cudaMemPool_t scratch_pool(int dev);
+
 // Optional device-side timing of the main scan kernel (bench.py roofline): when armed, launch_scan
 // brackets the main scan launch with a pair of CUDA events on the launching stream.
 void profile_scan_begin(cudaStream_t st);
