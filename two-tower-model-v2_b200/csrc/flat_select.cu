@@ -312,7 +312,7 @@ int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long l
   TT_CHECK_ARG(pl.main_slices <= FINALIZE_MAX_SLICES, "too many catalog slices");
   const size_t smem = (size_t)pl.cand_cap * 8 + (size_t)D * 4 + 16;
   count_launch();
-  if (nq <= num_sms() / 2) {
+  if (nq <= num_sms()) {          // one wide CTA per SM in a single wave
     TT_CHECK_CUDA(cudaFuncSetAttribute(flat_finalize_kernel<FIN_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TT_CHECK_CUDA(launch_pdl(flat_finalize_kernel<FIN_THREADS_WIDE>, dim3(nq), dim3(FIN_THREADS_WIDE), smem, st, qn, Xn, N, D, K,
                              id_offset, thr, eps, seg_cnt, reinterpret_cast<const uint2*>(cand), pl.main_slices, pl.seg_cap,
