@@ -159,7 +159,8 @@ def test_search_planner_invariants():
         assert p["supported"] == 1 and p["smem"] <= 227 * 1024 and p["stages"] >= 2
         # CTA pairs (256 queries per unit) exactly when nq > 128 (rows wider than 640 stream part of the query
         # block); single CTAs keep 128 resident queries while >= 3 full stages fit (D <= 512), else 64
-        want = 256 if nq > 128 else (64 if D > 512 else 128)
+        # (wide rows take pairs from nq > 64: one pass over the catalog instead of two M = 64 units)
+        want = 256 if (nq > 128 or (D > 512 and nq > 64)) else (64 if D > 512 else 128)
         assert p["unit_queries"] == want
         assert p["k_blocks"] == -(-D // 64) and p["tiles"] == -(-N // 256)
         assert p["query_units"] == -(-nq // want)
@@ -261,7 +262,7 @@ def test_search_planner_properties_random_shapes():
             return
         assert p["smem"] <= 227 * 1024 and p["stages"] >= 2 and p["stages"] <= 8
         assert p["unit_queries"] in (64, 128, 256)
-        assert (p["unit_queries"] == 256) == (nq > 128)
+        assert (p["unit_queries"] == 256) == (nq > 128 or (D > 512 and nq > 64))
         assert p["query_units"] * p["unit_queries"] >= nq
         assert 1 <= p["main_slices"] <= max(p["tiles"], 1) and p["main_slices"] <= 1024
         ws = lib.tt_flat_search_workspace_bytes(N, D, nq, K)

@@ -619,7 +619,11 @@ ScanPlan make_scan_plan(long long N, int D, int nq, int K) {
   const int b_full = BLOCK_N * BLOCK_K * 2, b_half = b_full / 2;
   pl.block_m = 128;
   pl.num_kb_res = pl.num_kb;
-  pl.pair = (nq > 128) && (sms >= 2);
+  // CTA pairs for nq > 128, and already for nq > 64 when the rows are too wide for a resident 128-query block
+  // (D > 512): two 64-query single-CTA units would read every catalog tile twice and run M = 64 MMAs at half rate
+  // (10M x 768, nq = 128: 0.81 of the HBM peak), the pair keeps one pass over the catalog.
+  const bool wide = budget - pl.num_kb * kb_bytes_m128 < 3 * b_full;
+  pl.pair = (nq > 128 || (wide && nq > 64)) && (sms >= 2);
   if (pl.pair) {
     // 2-CTA tiling, 128 queries per CTA.  The query block stays resident while it leaves room for 4 half-tile
     // stages (D <= 640); wider rows keep the leading K-blocks resident and stream the rest with the catalog.
