@@ -91,6 +91,16 @@ int tt_pool_attention_gather(const float* table, int64_t N, const float* row_log
                              float zero_row_logit, const int64_t* idx, const float* w,
                              float* out, int B, int S, int D, void* stream);
 
+/* Backward of the pooling op for training callers (src/models/two_tower.py:212, src/training/trainer.py:216-236): given
+ * g = dL/dout f32 [B,D] it recomputes y = sum_s coef_s x_s and writes
+ *   dx  f32 [B,S,D] (may be NULL) = coef_s * dy         - the pooling part of dL/dx
+ *   dw  f32 [B,S]                 = dL/dw
+ *   dlogit f32 [B,S] (attention: logits != NULL)        = dL/dlogit, which the caller feeds to the score MLP's own
+ *                                   backward (two plain GEMMs: dx += ..., dW1, db1, dW2, db2)
+ * with dy = (g - out (out.g)) / ||y|| (F.normalize), coefficients as in the forward.  D % 4 == 0, D <= 1024. */
+int tt_pool_backward(const float* x, const float* w, const float* logits, const float* g,
+                     float* dx, float* dw, float* dlogit, int B, int S, int D, void* stream);
+
 /* Pooling out of a row-SHARDED item table (BASELINE config C5: the catalog, which is the item table of the
  * /retrieve path - src/inference/encoder.py:276-303 pools the item embeddings of the history - is split over the
  * GPUs).  Owner computes: idx holds GLOBAL row ids; this rank reduces the positions whose row it owns

@@ -27,6 +27,7 @@ SIGNATURES = {
     "tt_attention_logits": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "tt_pool_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tt_pool_attention_gather": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tt_pool_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tt_pool_partial_gather": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_float, c_void_p, c_void_p,
                                        c_void_p, c_int, c_int, c_int, c_void_p]),
     "tt_pool_partial_merge": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),

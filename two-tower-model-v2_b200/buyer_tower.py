@@ -6,8 +6,8 @@ method names, argument meaning and exceptions.  The arithmetic runs in hand-writ
 kernels (csrc/pool.cu, csrc/attn_logits.cu) through the C-ABI; there is no CPU path: CPU tensors
 raise RuntimeError.
 
-Training callers work too: under autograd the forward still runs the fused kernels and the backward
-recomputes the reference formulation in eager torch (`_FusedPool`).
+Training callers work too: under autograd the forward still runs the fused kernels and the backward runs
+tt_pool_backward plus two plain GEMMs for the score MLP (`_FusedPool`).
 
 Beyond the reference surface: `precompute_item_logits` / `forward_gather` pool
 straight out of a device-resident item-embedding table given history row indices, so a request
@@ -24,8 +24,9 @@ from . import ops
 
 
 def _eager_pool(x: torch.Tensor, w: torch.Tensor, mlp=None) -> torch.Tensor:
-    """The reference arithmetic in differentiable torch ops (buyer_tower.py:58-66 / :85-99).  Used ONLY inside
-    the backward pass (recompute + autograd); the forward always runs the fused CUDA kernels."""
+    """The reference arithmetic in differentiable torch ops (buyer_tower.py:58-66 / :85-99).  Used ONLY inside the
+    backward pass of shapes the fused backward kernel does not take (D % 4 != 0 or D > 1024); the forward always
+    runs the fused CUDA kernels."""
     if mlp is None:
         nw = w.unsqueeze(-1) / (w.unsqueeze(-1).sum(dim=1, keepdim=True) + 1e-8)
         y = (x * nw).sum(dim=1)
@@ -39,8 +40,9 @@ def _eager_pool(x: torch.Tensor, w: torch.Tensor, mlp=None) -> torch.Tensor:
 
 class _FusedPool(torch.autograd.Function):
     """Forward: fused sm_100a kernels (no [B,S,D] temporary, no graph).  Backward (training callers of the
-    reference: src/models/two_tower.py:212, src/training/trainer.py:216-236): recompute the reference
-    formulation in eager torch and differentiate it - exact gradients, the cost of one eager forward+backward."""
+    reference: src/models/two_tower.py:212, src/training/trainer.py:216-236): tt_pool_backward - one fused kernel
+    for the normalisation / softmax / weighted-sum part (dx, dw, dlogit) - plus, in attention mode, the score MLP's
+    own backward as two plain GEMMs (autograd over the recomputed Linear-ReLU-Linear, a library GEMM)."""
 
     @staticmethod
     def forward(ctx, x, w, *mlp):
@@ -54,12 +56,30 @@ class _FusedPool(torch.autograd.Function):
     def backward(ctx, g):
         x, w, *mlp = ctx.saved_tensors
         needs = ctx.needs_input_grad
-        with torch.enable_grad():
-            ins = [t.detach().requires_grad_(needs[i]) for i, t in enumerate((x, w, *mlp))]
-            out = _eager_pool(ins[0], ins[1], tuple(ins[2:]) if mlp else None)
+        B, S, D = x.shape
+        if D % 4 != 0 or D > 1024:
+            with torch.enable_grad():
+                ins = [t.detach().requires_grad_(needs[i]) for i, t in enumerate((x, w, *mlp))]
+                out = _eager_pool(ins[0], ins[1], tuple(ins[2:]) if mlp else None)
+                wanted = [t for t in ins if t.requires_grad]
+                grads = iter(torch.autograd.grad(out, wanted, g.contiguous()))
+            return tuple(next(grads) if t.requires_grad else None for t in ins)
+        g = g.contiguous().float()
+        if not mlp:
+            dx, dw, _ = ops.pool_backward(x, w, None, g, need_dx=needs[0])
+            return (dx if needs[0] else None, dw if needs[1] else None)
+        W1, b1, W2, b2 = mlp
+        logits = ops.attention_logits(x.view(B * S, D), W1.contiguous(), b1.contiguous(), W2.reshape(-1).contiguous(),
+                                      b2.contiguous()).view(B, S)
+        dx, dw, dlogit = ops.pool_backward(x, w, logits, g, need_dx=needs[0])
+        with torch.enable_grad():          # d logits / d (x, W1, b1, W2, b2): plain GEMMs
+            ins = [x.detach().requires_grad_(needs[0])] + [t.detach().requires_grad_(needs[2 + i]) for i, t in enumerate(mlp)]
+            lg = (torch.relu(ins[0] @ ins[1].t() + ins[2]) @ ins[3].reshape(-1, 1) + ins[4]).squeeze(-1)
             wanted = [t for t in ins if t.requires_grad]
-            grads = iter(torch.autograd.grad(out, wanted, g.contiguous()))
-        return tuple(next(grads) if t.requires_grad else None for t in ins)
+            grads = iter(torch.autograd.grad(lg, wanted, dlogit)) if wanted else iter(())
+        mg = [next(grads) if t.requires_grad else None for t in ins]
+        gx = (dx + mg[0]) if needs[0] else None
+        return (gx, dw if needs[1] else None, *mg[1:])
 
 
 class BuyerTower(nn.Module):

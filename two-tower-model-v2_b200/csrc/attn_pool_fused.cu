@@ -161,9 +161,25 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
   if (warp == 0) {
     // =========================== TMA producer =====================================================
     if (lane == 0) {
+      // The boxes below are 128-byte segments at a 1536-byte stride and every row comes back nkb times: fetched from
+      // DRAM that way the stream ran at ~2.6 TB/s (r01 tf32 kernel and the first version of this one alike).  Rows of
+      // a tile are contiguous in memory, so the producer first asks L2 for whole tiles (plain contiguous bulk
+      // prefetches, a few tiles ahead): DRAM sees sequential 96 KB bursts, the boxes and the pooling re-read hit L2.
+      constexpr int PF_AHEAD = 3;
+      auto prefetch_tile = [&](int t) {
+        const long long rr = r0 + (long long)t * AF_TILE;
+        long long nbytes = ((rr + AF_TILE <= p.R) ? (long long)AF_TILE : (p.R - rr)) * p.D * 4;
+        const char* src = reinterpret_cast<const char*>(p.x + rr * p.D);
+        for (long long off = 0; off < nbytes; off += 16384) {
+          const unsigned int sz = (unsigned int)((nbytes - off < 16384) ? (nbytes - off) : 16384);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + off), "r"(sz) : "memory");
+        }
+      };
+      for (int t = 0; t < PF_AHEAD && t < ntiles; ++t) prefetch_tile(t);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
+        if (t + PF_AHEAD < ntiles) prefetch_tile(t + PF_AHEAD);
         const int row = (int)(r0 + (long long)t * AF_TILE);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(empty_raw + stage), phase ^ 1, 500 + stage);

@@ -398,6 +398,35 @@ select_threshold_kernel(const float* __restrict__ sample, int n, int npad, int r
 // per query.  The CTA stages a [slots x WQ] panel through shared memory with sector-sized reads, then
 // every warp runs r rounds of arg-max over its own column (each lane caches the best of its strided
 // values; only the winning lane rescans).  No block-wide barrier inside the rounds.
+// r rounds of "take the largest remaining value" over one warp's values v[0..n) (shared memory; lane l caches the best
+// of v[l], v[l+32], ... in best/bi).  A round is ONE redux.sync (warp max of the order-preserving uint32 image of the
+// lanes' bests) + one ballot to elect the owning lane, which drops its value and rescans its own stripe - instead of
+// a 5-step shuffle arg-max of (value, index) pairs.  Returns the r-th largest (-inf if fewer than r values); the
+// largest `out_n` are also written to out[] when given.
+__device__ __forceinline__ float warp_select_rounds(float* v, int n, int r, float best, int bi, int lane, float* out, int out_n) {
+  uint32_t kbest = (bi >= 0) ? float_to_ordered(best) : 0u;
+  float result = -INFINITY;
+  for (int round = 0; round < r; ++round) {
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, kbest);
+    const unsigned int owners = __ballot_sync(0xffffffffu, bi >= 0 && kbest == kmax);
+    result = owners ? ordered_to_float(kmax) : -INFINITY;
+    if (out && lane == 0 && round < out_n) out[round] = result;
+    if (owners && lane == __ffs(owners) - 1) {        // this lane owns the winner: drop it and rescan its own values
+      v[bi] = -INFINITY;
+      float nb = -INFINITY;
+      int ni = -1;
+      for (int i = lane; i < n; i += 32) {
+        const float x = v[i];
+        if (x > nb) { nb = x; ni = i; }
+      }
+      best = nb; bi = ni;
+      kbest = (bi >= 0) ? float_to_ordered(best) : 0u;
+    }
+    __syncwarp();
+  }
+  return result;
+}
+
 constexpr int SEL_WQ = 8;   // queries (warps) per CTA
 __global__ void __launch_bounds__(SEL_WQ * 32)
 select_threshold_tile_kernel(const float* __restrict__ sample, int slots, int ld, int nq, int r, float* __restrict__ thr,
@@ -428,28 +457,7 @@ select_threshold_tile_kernel(const float* __restrict__ sample, int slots, int ld
     const float x = v[i];
     if (x > best) { best = x; bi = i; }
   }
-  float result = -INFINITY;
-  for (int round = 0; round < r; ++round) {
-    float wb = best;
-    int wi = bi;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, wb, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-      if (ob > wb || (ob == wb && oi > wi)) { wb = ob; wi = oi; }
-    }
-    result = (wi >= 0) ? wb : -INFINITY;
-    if (topr && lane == 0 && round < topr_ld) topr[(size_t)q * topr_ld + round] = result;
-    if (wi >= 0 && wi == bi) {      // this lane owns the winner: drop it and rescan its own values
-      v[wi] = -INFINITY;
-      best = -INFINITY; bi = -1;
-      for (int i = lane; i < slots; i += 32) {
-        const float x = v[i];
-        if (x > best) { best = x; bi = i; }
-      }
-    }
-    __syncwarp();
-  }
+  const float result = warp_select_rounds(v, slots, r, best, bi, lane, topr ? topr + (size_t)q * topr_ld : nullptr, topr_ld);
   if (thr && lane == 0) thr[q] = result;
   if (topr) for (int i = r + lane; i < topr_ld; i += 32) topr[(size_t)q * topr_ld + i] = -INFINITY;
 }
@@ -478,27 +486,7 @@ select_threshold_gathered_kernel(const float* __restrict__ gathered, int G, int 
     if (x > best) { best = x; bi = i; }
   }
   __syncwarp();
-  float result = -INFINITY;
-  for (int round = 0; round < r; ++round) {
-    float wb = best;
-    int wi = bi;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, wb, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-      if (ob > wb || (ob == wb && oi > wi)) { wb = ob; wi = oi; }
-    }
-    result = (wi >= 0) ? wb : -INFINITY;
-    if (wi >= 0 && wi == bi) {
-      v[wi] = -INFINITY;
-      best = -INFINITY; bi = -1;
-      for (int i = lane; i < n; i += 32) {
-        const float x = v[i];
-        if (x > best) { best = x; bi = i; }
-      }
-    }
-    __syncwarp();
-  }
+  const float result = warp_select_rounds(v, n, r, best, bi, lane, nullptr, 0);
   if (lane == 0) thr[q] = result;
 }
 

@@ -126,6 +126,12 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
     const uint2 e = cand[((size_t)q * nslices + lo) * seg_cap + (i - s_off[lo])];
     key[i] = make_key(__uint_as_float(e.x), e.y);
+    // Small batches are latency-bound: start pulling the candidate's fp32 row into L2 now, so that the radix select
+    // and the pruning below hide the DRAM latency of the rescoring pass (n ~ 1000 rows of D*4 bytes: ~1.5 MB).
+    if (FIN_THREADS == FIN_THREADS_WIDE && (long long)e.y < N) {
+      const char* rowp = reinterpret_cast<const char*>(Xn + (long long)e.y * D);
+      for (int off = 0; off < D * 4; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + off));
+    }
   }
   __syncthreads();
 

@@ -480,3 +480,143 @@ extern "C" __attribute__((visibility("default"))) int tt_pool_partial_merge(cons
   TT_CHECK_LAUNCH();
   return TT_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Backward of the pooling op (training callers of the reference: src/models/two_tower.py:212,
+// src/training/trainer.py:216-236).  One warp per buyer, two passes over the buyer's rows (the second one hits L2):
+//   y = sum_s coef_s x_s,  out = y / max(||y||, 1e-12)                        (forward, buyer_tower.py:58-66 / :89-99)
+//   dy = (g - out (out.g)) / ||y||            (dy = g / 1e-12 below the clamp, as torch.nn.functional.normalize)
+//   dx_s = coef_s dy  (pooling part),  t_s = x_s . dy
+//   weighted_avg: dw_s = (t_s - y.dy) / (sum w + 1e-8)
+//   attention   : dc_s = coef_s (t_s - y.dy);  dlogit_s = w_s dc_s;  dw_s = logit_s dc_s
+// The score MLP's own backward (dlogit -> dx, dW1, db1, dW2, db2) is two plain GEMMs and stays with the caller.
+namespace tt {
+
+struct PoolBwdParams {
+  const float* x; const float* w; const float* logits; const float* g;
+  float* dx; float* dw; float* dlogit;
+  int B, S, D;
+};
+
+template <int NV, bool ATTN>
+__global__ void __launch_bounds__(128)
+pool_backward_kernel(const PoolBwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= p.B) return;
+  const int S = p.S, D = p.D, nvalid4 = D >> 2;
+  const float* wb = p.w + (long long)b * S;
+  const float* lb = ATTN ? p.logits + (long long)b * S : nullptr;
+  const float4* xb = reinterpret_cast<const float4*>(p.x + (long long)b * S * D);
+  // coefficients
+  float m = -INFINITY, tot = 0.f;
+  if (ATTN) {
+    for (int s = lane; s < S; s += 32) m = fmaxf(m, __ldg(lb + s) * __ldg(wb + s));
+    m = warp_max(m);
+    for (int s = lane; s < S; s += 32) tot += expf(__ldg(lb + s) * __ldg(wb + s) - m);
+    tot = warp_sum(tot);
+  } else {
+    for (int s = lane; s < S; s += 32) tot += __ldg(wb + s);
+    tot = warp_sum(tot) + 1e-8f;
+  }
+  auto coef_of = [&](int s) -> float {
+    return ATTN ? expf(__ldg(lb + s) * __ldg(wb + s) - m) / tot : __ldg(wb + s) / tot;
+  };
+  // pass 1: y
+  float4 y[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) y[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < S; ++s) {
+    const float c = coef_of(s);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c4 = v * 32 + lane;
+      if (c4 < nvalid4) {
+        const float4 xv = __ldg(xb + (long long)s * nvalid4 + c4);
+        y[v].x = fmaf(xv.x, c, y[v].x); y[v].y = fmaf(xv.y, c, y[v].y);
+        y[v].z = fmaf(xv.z, c, y[v].z); y[v].w = fmaf(xv.w, c, y[v].w);
+      }
+    }
+  }
+  float ss = 0.f, yg = 0.f;
+  float4 gv[NV];
+  const float4* gb = reinterpret_cast<const float4*>(p.g + (long long)b * D);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c4 = v * 32 + lane;
+    gv[v] = (c4 < nvalid4) ? __ldg(gb + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss += y[v].x * y[v].x + y[v].y * y[v].y + y[v].z * y[v].z + y[v].w * y[v].w;
+    yg += y[v].x * gv[v].x + y[v].y * gv[v].y + y[v].z * gv[v].z + y[v].w * gv[v].w;
+  }
+  ss = warp_sum(ss);
+  yg = warp_sum(yg);
+  const float nrm = sqrtf(ss);
+  // dy = (g - out (out.g)) / n with out = y / n;  below the eps clamp out = y / eps and dy = g / eps
+  float4 dy[NV];
+  float ydy = 0.f;
+  const bool clamped = !(nrm > 1e-12f);
+  const float inv = clamped ? 1e12f : 1.0f / nrm;
+  const float proj = clamped ? 0.f : yg * inv * inv;          // (out.g)/n * (1/n) applied to y
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    dy[v].x = (gv[v].x - y[v].x * proj) * inv; dy[v].y = (gv[v].y - y[v].y * proj) * inv;
+    dy[v].z = (gv[v].z - y[v].z * proj) * inv; dy[v].w = (gv[v].w - y[v].w * proj) * inv;
+    ydy += y[v].x * dy[v].x + y[v].y * dy[v].y + y[v].z * dy[v].z + y[v].w * dy[v].w;
+  }
+  ydy = warp_sum(ydy);
+  // pass 2: t_s = x_s . dy, dx_s = coef_s dy
+  float4* dxb = p.dx ? reinterpret_cast<float4*>(p.dx + (long long)b * S * D) : nullptr;
+  for (int s = 0; s < S; ++s) {
+    const float c = coef_of(s);
+    float t = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c4 = v * 32 + lane;
+      if (c4 < nvalid4) {
+        const float4 xv = __ldg(xb + (long long)s * nvalid4 + c4);
+        t += xv.x * dy[v].x + xv.y * dy[v].y + xv.z * dy[v].z + xv.w * dy[v].w;
+        if (dxb) dxb[(long long)s * nvalid4 + c4] = make_float4(c * dy[v].x, c * dy[v].y, c * dy[v].z, c * dy[v].w);
+      }
+    }
+    t = warp_sum(t);
+    if (lane == 0) {
+      if (ATTN) {
+        const float dc = c * (t - ydy);
+        p.dlogit[(long long)b * S + s] = __ldg(wb + s) * dc;
+        p.dw[(long long)b * S + s] = __ldg(lb + s) * dc;
+      } else {
+        p.dw[(long long)b * S + s] = (t - ydy) / tot;
+      }
+    }
+  }
+}
+
+template <bool ATTN>
+static int launch_pool_bwd(const PoolBwdParams& p, cudaStream_t st) {
+  const int grid = (p.B + 3) / 4;
+  switch ((p.D + 127) / 128) {
+    case 1: pool_backward_kernel<1, ATTN><<<grid, 128, 0, st>>>(p); break;
+    case 2: pool_backward_kernel<2, ATTN><<<grid, 128, 0, st>>>(p); break;
+    case 3: pool_backward_kernel<3, ATTN><<<grid, 128, 0, st>>>(p); break;
+    case 4: pool_backward_kernel<4, ATTN><<<grid, 128, 0, st>>>(p); break;
+    case 5: case 6: pool_backward_kernel<6, ATTN><<<grid, 128, 0, st>>>(p); break;
+    default: pool_backward_kernel<8, ATTN><<<grid, 128, 0, st>>>(p); break;
+  }
+  TT_CHECK_LAUNCH();
+  return TT_OK;
+}
+
+}  // namespace tt
+
+extern "C" __attribute__((visibility("default"))) int tt_pool_backward(const float* x, const float* w, const float* logits, const float* g,
+                                                          float* dx, float* dw, float* dlogit, int B, int S, int D, void* stream) {
+  TT_CHECK_ARG(x && w && g && dw, "null pointer");
+  TT_CHECK_ARG((logits == nullptr) == (dlogit == nullptr), "logits and dlogit go together (attention mode)");
+  TT_CHECK_ARG(B >= 0 && S >= 1 && D >= 4 && D % 4 == 0 && D <= 1024, "need B >= 0, S >= 1, D % 4 == 0, 4 <= D <= 1024");
+  TT_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0,
+               "x, g and dx must be 16-byte aligned");
+  if (B == 0) return TT_OK;
+  PoolBwdParams p{};
+  p.x = x; p.w = w; p.logits = logits; p.g = g; p.dx = dx; p.dw = dw; p.dlogit = dlogit; p.B = B; p.S = S; p.D = D;
+  return logits ? launch_pool_bwd<true>(p, (cudaStream_t)stream) : launch_pool_bwd<false>(p, (cudaStream_t)stream);
+}

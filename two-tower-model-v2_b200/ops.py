@@ -104,6 +104,20 @@ def pool_attention_gather(table: torch.Tensor, row_logits: torch.Tensor, zero_ro
     return out
 
 
+def pool_backward(x: torch.Tensor, w: torch.Tensor, logits, g: torch.Tensor, need_dx: bool = True):
+    """Backward of the pooling op (tt_pool_backward): -> (dx [B,S,D] or None, dw [B,S], dlogit [B,S] or None)."""
+    B, S, D = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty((B, S), device=x.device, dtype=torch.float32)
+    dlogit = torch.empty((B, S), device=x.device, dtype=torch.float32) if logits is not None else None
+    with torch.cuda.device(x.device):
+        _native.check(_native.load().tt_pool_backward(
+            x.data_ptr(), w.data_ptr(), 0 if logits is None else logits.data_ptr(), g.data_ptr(),
+            0 if dx is None else dx.data_ptr(), dw.data_ptr(), 0 if dlogit is None else dlogit.data_ptr(), B, S, D,
+            _stream()), "tt_pool_backward")
+    return dx, dw, dlogit
+
+
 def pool_partial_gather(table: torch.Tensor, row_lo: int, n_total: int, owns_invalid: bool, row_logits, zero_row_logit: float,
                         idx: torch.Tensor, w: torch.Tensor, partial: torch.Tensor = None) -> torch.Tensor:
     """Owner-computes partial pooling over this rank's rows of a sharded item table -> partial f32 [B, D+4]
@@ -211,4 +225,4 @@ def shard_merge(gathered: torch.Tensor, off_scores: int, off_ids: int, off_bound
 
 
 __all__ = ["shard_merge", "flat_build", "flat_search", "flat_search_exact", "pool_weighted", "pool_weighted_gather", "attention_logits", "pool_attention",
-           "pool_attention_gather", "pool_attention_fused", "pool_partial_gather", "pool_partial_merge", "topk_merge", "_f32c", "_stream"]
+           "pool_attention_gather", "pool_attention_fused", "pool_backward", "pool_partial_gather", "pool_partial_merge", "topk_merge", "_f32c", "_stream"]
