@@ -78,6 +78,7 @@ struct AttnFusedParams {
   int* flag;               // raised when a value leaves the fp16 range
   long long R;
   int B, S, D, H, nkb;
+  int mode;                // bit 0: TMA loads with the L2 evict_last hint; bit 1: bulk L2 prefetch of whole tiles ahead
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -165,8 +166,10 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
       // DRAM that way the stream ran at ~2.6 TB/s (r01 tf32 kernel and the first version of this one alike).  Rows of
       // a tile are contiguous in memory, so the producer first asks L2 for whole tiles (plain contiguous bulk
       // prefetches, a few tiles ahead): DRAM sees sequential 96 KB bursts, the boxes and the pooling re-read hit L2.
+      const bool l2_keep = (p.mode & 1) != 0, l2_prefetch = (p.mode & 2) != 0;
       constexpr int PF_AHEAD = 3;
       auto prefetch_tile = [&](int t) {
+        if (!l2_prefetch) return;
         const long long rr = r0 + (long long)t * AF_TILE;
         long long nbytes = ((rr + AF_TILE <= p.R) ? (long long)AF_TILE : (p.R - rr)) * p.D * 4;
         const char* src = reinterpret_cast<const char*>(p.x + rr * p.D);
@@ -186,8 +189,13 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
           const uint32_t fb = smem_u32(full_raw + stage);
           const uint32_t dst = smem_u32(raw_ring + (size_t)stage * AF_RAW_STAGE);
           mbar_arrive_expect_tx(fb, (uint32_t)AF_RAW_STAGE);
-          tma_load_2d(dst, &tmap_x, fb, kb * 64, row);
-          tma_load_2d(dst + AF_RAW_STAGE / 2, &tmap_x, fb, kb * 64 + 32, row);
+          if (l2_keep) {      // the rows are read again by the pooling warps: ask L2 to keep them (evict_last)
+            tma_load_2d_hint(dst, &tmap_x, fb, kb * 64, row, kEvictLast);
+            tma_load_2d_hint(dst + AF_RAW_STAGE / 2, &tmap_x, fb, kb * 64 + 32, row, kEvictLast);
+          } else {
+            tma_load_2d(dst, &tmap_x, fb, kb * 64, row);
+            tma_load_2d(dst + AF_RAW_STAGE / 2, &tmap_x, fb, kb * 64 + 32, row);
+          }
           if (++stage == AF_RAW_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -562,6 +570,11 @@ attn_pool_fallback_kernel(const float* __restrict__ x, const float* __restrict__
   }
 }
 
+static int fused_mode() {
+  static const int m = [] { const char* e = getenv("TT_B200_ATTN_MODE"); return e ? atoi(e) : 1; }();
+  return m;
+}
+
 struct FusedWs { size_t wp, meta, total; };
 static FusedWs fused_ws_layout(int nkb) {
   FusedWs w{};
@@ -602,6 +615,7 @@ int launch_attn_logits_fused(const float* x, long long R, int D, const float* W1
     AttnFusedParams p{};
     p.x = x; p.logits_out = logits; p.Wp = Wp; p.b1 = b1; p.W2 = W2; p.b2 = b2; p.inv_scale = inv_scale; p.flag = flag;
     p.R = R; p.B = (int)R; p.S = 1; p.D = D; p.H = H; p.nkb = nkb;
+    p.mode = 0;
     const size_t smem = (size_t)AF_RAW_STAGES * AF_RAW_STAGE + (size_t)AF_B_STAGES * AF_B_STAGE + AF_RMAX * sizeof(float) +
                         2 * 4 * AF_TILE * sizeof(float) + 512 + 1024;
     const long long tiles = (R + AF_TILE - 1) / AF_TILE;
@@ -667,6 +681,7 @@ extern "C" __attribute__((visibility("default"))) int tt_pool_attention_fused(co
     p.x = x + bdone * S * D; p.w = w + bdone * S; p.out = out + bdone * D; p.Wp = Wp;
     p.b1 = b1; p.W2 = W2; p.b2 = b2; p.inv_scale = inv_scale; p.flag = flag;
     p.R = nb * S; p.B = (int)nb; p.S = S; p.D = D; p.H = H; p.nkb = nkb;
+    p.mode = fused_mode();
     const int grid = (int)(nb < sms ? nb : sms);
     // programmatic dependent launch: the x stream (TMA, splitters) starts under the weight-preparation kernel's tail;
     // only the epilogue warps (W1 pieces, scale) and the flag wait for it.  The preparation kernel itself is a plain
