@@ -78,7 +78,9 @@ struct AttnFusedParams {
   int* flag;               // raised when a value leaves the fp16 range
   long long R;
   int B, S, D, H, nkb;
-  int mode;                // bit 0: TMA loads with the L2 evict_last hint; bit 1: bulk L2 prefetch of whole tiles ahead
+  int mode;                // bit 0: TMA loads with the L2 evict_last hint; bit 1: bulk L2 prefetch of whole tiles ahead;
+                           // bits 2-4 (TT_B200_ATTN_MODE, timing experiments only, wrong results): 4 no cross MMAs,
+                           // 8 no MMAs at all, 16 no fp16 split arithmetic
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -224,9 +226,9 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
             const uint32_t a_hi = tmem_base + w_hi_col + (uint32_t)((kb * 4 + k) * 8);
             const uint32_t a_lo = tmem_base + w_lo_col + (uint32_t)((kb * 4 + k) * 8);
             const uint32_t first = (uint32_t)((kb | k) != 0);
-            mma_f16_ts(d_main, a_hi, xh + koff, idesc, first);                 // hi.hi   -> main accumulator
-            mma_f16_ts(d_cross, a_lo, xh + koff, idesc, first);                // lo_w.hi_x
-            mma_f16_ts(d_cross, a_hi, xl + koff, idesc, 1u);                   // hi_w.lo_x -> cross accumulator
+            if (!(p.mode & 8)) mma_f16_ts(d_main, a_hi, xh + koff, idesc, first);                 // hi.hi   -> main accumulator
+            if (!(p.mode & 12)) mma_f16_ts(d_cross, a_lo, xh + koff, idesc, first);                // lo_w.hi_x
+            if (!(p.mode & 12)) mma_f16_ts(d_cross, a_hi, xl + koff, idesc, 1u);                   // hi_w.lo_x -> cross accumulator
           }
           mma_commit(smem_u32(empty_b + stage));
           if (kb == nkb - 1) mma_commit(smem_u32(tmem_full));
@@ -348,8 +350,8 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
       uint8_t* lo_tile = hi_tile + AF_B_STAGE / 2;
 #pragma unroll
       for (int i = 0; i < UPT; ++i) {
-        uint4 hi, lo;
-        split8(fa[i], fb[i], hi, lo, mabs);
+        uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+        if (!(p.mode & 16)) split8(fa[i], fb[i], hi, lo, mabs);
         *reinterpret_cast<uint4*>(hi_tile + row[i] * 128 + cpos[i]) = hi;
         *reinterpret_cast<uint4*>(lo_tile + row[i] * 128 + cpos[i]) = lo;
       }
@@ -615,7 +617,7 @@ int launch_attn_logits_fused(const float* x, long long R, int D, const float* W1
     AttnFusedParams p{};
     p.x = x; p.logits_out = logits; p.Wp = Wp; p.b1 = b1; p.W2 = W2; p.b2 = b2; p.inv_scale = inv_scale; p.flag = flag;
     p.R = R; p.B = (int)R; p.S = 1; p.D = D; p.H = H; p.nkb = nkb;
-    p.mode = 0;
+    p.mode = fused_mode() & ~3;      // (diagnostic bits only)
     const size_t smem = (size_t)AF_RAW_STAGES * AF_RAW_STAGE + (size_t)AF_B_STAGES * AF_B_STAGE + AF_RMAX * sizeof(float) +
                         2 * 4 * AF_TILE * sizeof(float) + 512 + 1024;
     const long long tiles = (R + AF_TILE - 1) / AF_TILE;
