@@ -25,13 +25,19 @@ def timeit(fn, iters=20):
 
 
 def main():
-    B, S, D = 4096, 50, 384
+    import os
+    B, S, D = int(os.environ.get('TT_DIAG_B', 4096)), 50, 384
     g = torch.Generator(device="cuda").manual_seed(99)
     x = torch.randn((B, S, D), device="cuda", generator=g)
     w = torch.tensor([1.0, 5.0, 10.0], device="cuda")[torch.randint(0, 3, (B, S), device="cuda", generator=g)]
     torch.manual_seed(0)
     m = pkg.BuyerTower(D, "attention").cuda()
     W1, b1, W2, b2 = m._mlp_params(x.device)
+    import os
+    if os.environ.get("TT_DIAG_LOGITS_ONLY"):
+        with torch.no_grad():
+            print(json.dumps({"logits_only_us": timeit(lambda: ops.attention_logits(x.view(B * S, D), W1, b1, W2, b2))}))
+        return
     with torch.no_grad():
         out = {"fused_us": timeit(lambda: m(x, w)),
                "logits_only_us": timeit(lambda: ops.attention_logits(x.view(B * S, D), W1, b1, W2, b2)),
