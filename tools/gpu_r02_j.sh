@@ -12,7 +12,7 @@ timeout 200 $TR --master-port 29513 tools/check_sharded.py 3000 64 50 1000 2>&1 
 echo "== check_sharded_retrieve"; timeout 300 $TR --master-port 29514 tools/check_sharded_retrieve.py 4000000 384 256 50 100 2>&1 | grep -v "^W\|^\*\*\*" | tail -6 | tee -a $O/r02j_check_sharded_n$N.log
 echo "== bench N=$N"
 for W in headline c4 c5; do
-  timeout 500 $TR --master-port 2952$RANDOM bench.py --gpus $N --workload $W --steps 20 --warmup 4 > $O/r02j_bench_n${N}_$W.log 2> $O/r02j_bench_n${N}_$W.err; echo "$W rc=$?"; grep -v "^W\|^\*\*\*\|^$" $O/r02j_bench_n${N}_$W.err | tail -5
+  timeout 500 $TR --master-port $((29560 + RANDOM % 300)) bench.py --gpus $N --workload $W --steps 20 --warmup 4 > $O/r02j_bench_n${N}_$W.log 2> $O/r02j_bench_n${N}_$W.err; echo "$W rc=$?"; grep -v "^W\|^\*\*\*\|^$" $O/r02j_bench_n${N}_$W.err | tail -5
   python - <<PY
 import json
 try:

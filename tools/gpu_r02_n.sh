@@ -1,0 +1,18 @@
+#!/bin/bash
+# bench at N GPUs for the three workloads (headline, c4, c5); N = $1
+N=${1:-2}
+mkdir -p gpurun_out
+O=gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node $N"
+for W in headline c4 c5; do
+  timeout 500 $TR --master-port $((29560 + RANDOM % 300)) bench.py --gpus $N --workload $W --steps 20 --warmup 4 > $O/r02n_bench_n${N}_$W.log 2> $O/r02n_bench_n${N}_$W.err; echo "$W rc=$?"; grep -v "^W\|^\*\*\*\|^$\|OMP_NUM\|NCCL version" $O/r02n_bench_n${N}_$W.err | tail -5
+  python - <<PY
+import json
+try:
+    r=json.loads([l for l in open("gpurun_out/r02n_bench_n${N}_$W.log") if l.startswith("{")][-1])
+    rf=r["roofline"] or {}
+    print("$W", r["metric"], "value", round(r["value"]), "e2e", round(r["e2e"]["value"]), "ms", round(r["ms_per_step"],3), {k:(round(rf[k],4) if isinstance(rf.get(k),float) else rf.get(k)) for k in ("frac","kernel_ms","kernel_share_of_step")}, "parity", r["parity"]["ok_all_ranks"], "unc", r["uncertified_queries"], r.get("latency_batch1_ms"), r["clocks"])
+except Exception as e:
+    print("$W bench parse failed", e)
+PY
+done

@@ -45,6 +45,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <string.h>
 #include "tt_common.cuh"
 #include "sm100_ptx.cuh"
 #include "flat_internal.cuh"
@@ -113,23 +114,35 @@ __device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi
     const __half2 ll = __floats2half2_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
     h[i] = *reinterpret_cast<const uint32_t*>(&hh);
     l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-    // NaN fails the comparison too
-    mabs = (fabsf(v[2 * i]) <= AF_F16_MAX && fabsf(v[2 * i + 1]) <= AF_F16_MAX) ? mabs : INFINITY;
+    mabs = fmaxf(mabs, fmaxf(fabsf(v[2 * i]), fabsf(v[2 * i + 1])));      // (a NaN propagates through the MMA like in fp32)
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// acc[0..7] += coef * (hi + lo)  for the 8 fp16 pairs of one 16-byte chunk
-__device__ __forceinline__ void fma_chunk(float (&acc)[8], const uint4 hi, const uint4 lo, const float coef) {
-  const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
-    acc[2 * i] = fmaf(a.x + b.x, coef, acc[2 * i]);
-    acc[2 * i + 1] = fmaf(a.y + b.y, coef, acc[2 * i + 1]);
-  }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ __half2 as_half2(uint32_t u) {
+  __half2 h;
+  memcpy(&h, &u, sizeof(h));
+  return h;
+}
+// one 16-byte chunk (8 columns) of one row:  acc += coef * hi (fp32),  accl += coef * lo (packed fp16)
+__device__ __forceinline__ void fma_chunk(float (&acc)[8], __half2 (&accl)[4], const uint4 hi, const uint4 lo, const float coef) {
+  const __half2 ch = __float2half2_rn(coef);
+  const float2 a0 = __half22float2(as_half2(hi.x)), a1 = __half22float2(as_half2(hi.y));
+  const float2 a2 = __half22float2(as_half2(hi.z)), a3 = __half22float2(as_half2(hi.w));
+  acc[0] = fmaf(a0.x, coef, acc[0]); acc[1] = fmaf(a0.y, coef, acc[1]);
+  acc[2] = fmaf(a1.x, coef, acc[2]); acc[3] = fmaf(a1.y, coef, acc[3]);
+  acc[4] = fmaf(a2.x, coef, acc[4]); acc[5] = fmaf(a2.y, coef, acc[5]);
+  acc[6] = fmaf(a3.x, coef, acc[6]); acc[7] = fmaf(a3.y, coef, acc[7]);
+  accl[0] = __hfma2(as_half2(lo.x), ch, accl[0]);
+  accl[1] = __hfma2(as_half2(lo.y), ch, accl[1]);
+  accl[2] = __hfma2(as_half2(lo.z), ch, accl[2]);
+  accl[3] = __hfma2(as_half2(lo.w), ch, accl[3]);
 }
 
 template <bool POOL>
@@ -201,7 +214,13 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
   } else if (warp == AF_MMA_WARP) {
     // =========================== MMA issuer =======================================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16_f32(AF_M, AF_TILE);
+      // per K = 16 step TWO MMAs: the hi and lo tiles of a K-block are adjacent in shared memory (same 8-row-group
+      // stride), so one N = 128 MMA with A = hi_w computes hi_w.[hi_x | lo_x] into the main (columns 0-63) and the
+      // cross-term accumulator (columns 64-127) at once; a second N = 64 MMA adds lo_w.hi_x to the cross terms.
+      // A tensor-memory A operand costs ~100 cycles per MMA whatever N is (64 B/cycle TMEM read), so 2 instead of 3
+      // MMAs per step is a third less tensor time.
+      constexpr uint32_t idesc128 = make_idesc_f16_f32(AF_M, 2 * AF_TILE);
+      constexpr uint32_t idesc64 = make_idesc_f16_f32(AF_M, AF_TILE);
       mbar_wait(smem_u32(w_bar), 0, 510);
       tc_fence_after();
       const uint32_t d_main = tmem_base, d_cross = tmem_base + (uint32_t)AF_TILE;
@@ -216,17 +235,15 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
           AF_TR(t, 14 + kb);
           tc_fence_after();
           const uint32_t base = smem_u32(tiles + (size_t)buf * buf_bytes + (size_t)kb * AF_KB_BYTES);
-          const uint64_t xh = make_smem_desc_sw128(base);
-          const uint64_t xl = make_smem_desc_sw128(base + AF_KB_BYTES / 2);
+          const uint64_t xh = make_smem_desc_sw128(base);          // N = 128: rows 0-63 = hi tile, rows 64-127 = lo tile
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t koff = (uint64_t)((ks * 16 * 2) >> 4);               // 32 bytes per K = 16 step
             const uint32_t a_hi = tmem_base + w_hi_col + (uint32_t)((kb * 4 + ks) * 8);
             const uint32_t a_lo = tmem_base + w_lo_col + (uint32_t)((kb * 4 + ks) * 8);
             const uint32_t first = (uint32_t)((kb | ks) != 0);
-            if (!(p.mode & 8)) mma_f16_ts(d_main, a_hi, xh + koff, idesc, first);                 // hi.hi   -> main accumulator
-            if (!(p.mode & 12)) mma_f16_ts(d_cross, a_lo, xh + koff, idesc, first);               // lo_w.hi_x
-            if (!(p.mode & 12)) mma_f16_ts(d_cross, a_hi, xl + koff, idesc, 1u);                  // hi_w.lo_x -> cross accumulator
+            if (!(p.mode & 8)) mma_f16_ts(d_main, a_hi, xh + koff, idesc128, first);              // hi_w.[hi_x | lo_x]
+            if (!(p.mode & 12)) mma_f16_ts(d_cross, a_lo, xh + koff, idesc64, 1u);                // + lo_w.hi_x
           }
         }
         mma_commit(smem_u32(acc_full));
@@ -362,23 +379,33 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
       }
     }
     pdl_wait();      // the weight-preparation kernel cleared the flag
-    if (!(mabs <= AF_F16_MAX)) atomicOr(p.flag, 1);
+    // out of the fp16 range, or large enough for the fp16 sum of the lo pieces of S rows to overflow
+    if (!(mabs <= AF_F16_MAX) || (POOL && !(mabs * (float)p.S <= 1.0e8f))) atomicOr(p.flag, 1);
   } else if (warp >= AF_POOL_WARP0 && warp - AF_POOL_WARP0 < nkb) {
     // =========================== pooling: warp pw owns columns [64 pw, 64 pw + 64) ======================
     const int pw = warp - AF_POOL_WARP0;
     const int c = lane & 7, rs = lane >> 3;        // 16-byte chunk (8 columns) / row subset: rows n = 4g + rs
     const int S = p.S;
+    // sum_s a_s x_s with x = (hi + lo) / 16: the hi pieces accumulate in fp32, the lo pieces (2^-11 of hi) in packed
+    // fp16 (their rounding is 2^-22 of the sum; the splitters flag inputs large enough to overflow an fp16 sum)
     float acc[8];
+    __half2 accl[4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) accl[i] = __float2half2_rn(0.f);
     float m_run = -INFINITY, l_run = 0.f;
     int nfin = 0;
+    int next_end = S;                               // CTA-local row at which the current buyer ends
+    int bl = 0;                                     // current buyer, CTA-local
     const float* wrow = POOL ? p.w + r0 : nullptr;
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    const int nrows_i = (int)nrows;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const uint32_t k = (uint32_t)(t >> 1);
-      const long long n0 = (long long)t * AF_TILE;
-      const int nvalid = (int)((nrows - n0 < AF_TILE) ? (nrows - n0) : AF_TILE);
+      const int n0 = t * AF_TILE;
+      const int nvalid = (nrows_i - n0 < AF_TILE) ? (nrows_i - n0) : AF_TILE;
       float w0 = 0.f, w1 = 0.f;
       if (POOL) {                                   // event weights of the tile's rows: in flight while the logits are computed
         if (lane < nvalid) w0 = __ldg(wrow + n0 + lane);
@@ -387,14 +414,13 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
       mbar_wait_warp(smem_u32(logits_full + buf), k & 1u, 570 + buf);
       if (pw == 0 && lane == 0) AF_TR(t, 23);
       if (POOL) {
-        const uint8_t* hi_tile = tiles + (size_t)buf * buf_bytes + (size_t)pw * AF_KB_BYTES;
+        const uint32_t base = tiles_u32 + (uint32_t)buf * (uint32_t)buf_bytes + (uint32_t)pw * AF_KB_BYTES;
         const float z0 = (lane < nvalid) ? logits_s[buf * AF_TILE + lane] * w0 : -INFINITY;
         const float z1 = (lane + 32 < nvalid) ? logits_s[buf * AF_TILE + lane + 32] * w1 : -INFINITY;
         int n_lo = 0;
         while (n_lo < nvalid) {
-          const long long bl = (n0 + n_lo) / S;                          // buyer (local) of row n_lo
-          const long long bend = (bl + 1) * S - n0;                      // its end, in tile coordinates
-          const int n_hi = (int)(bend < nvalid ? bend : nvalid);
+          const int bend = next_end - n0;                                 // end of the current buyer, tile coordinates
+          const int n_hi = bend < nvalid ? bend : nvalid;
           // ---- online softmax step (buyer_tower.py:89-92) -----------------------------------------
           const bool in0 = lane >= n_lo && lane < n_hi, in1 = lane + 32 >= n_lo && lane + 32 < n_hi;
           const float smax = warp_max(fmaxf(in0 ? z0 : -INFINITY, in1 ? z1 : -INFINITY));
@@ -403,17 +429,33 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
           const float p0 = in0 ? expf(z0 - m_new) : 0.f, p1 = in1 ? expf(z1 - m_new) : 0.f;
           l_run = l_run * scale + warp_sum(p0 + p1);
           m_run = m_new;
+          if (scale != 1.f) {
+            const __half2 sh = __float2half2_rn(scale);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] *= scale;
-          // ---- weighted row sum (buyer_tower.py:96) from the hi/lo tiles --------------------------
+            for (int i = 0; i < 8; ++i) acc[i] *= scale;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) accl[i] = __hmul2(accl[i], sh);
+          }
+          // ---- weighted row sum (buyer_tower.py:96) from the hi/lo tiles, two 4-row groups per step ----
           const int g_end = (n_hi - 1) >> 2;
-          for (int g = n_lo >> 2; g <= g_end; ++g) {
-            const int n = 4 * g + rs;
-            const float pv = __shfl_sync(0xffffffffu, (g < 8) ? p0 : p1, n & 31);     // 0 outside [n_lo, n_hi)
-            const uint8_t* a = hi_tile + n * 128 + ((c ^ (n & 7)) << 4);
-            const uint4 hi = *reinterpret_cast<const uint4*>(a);
-            const uint4 lo = *reinterpret_cast<const uint4*>(a + AF_KB_BYTES / 2);
-            fma_chunk(acc, hi, lo, pv);
+          int g = n_lo >> 2;
+          for (; g < g_end; g += 2) {
+            const int nA = 4 * g + rs, nB = nA + 4;
+            const float pA = __shfl_sync(0xffffffffu, (g < 8) ? p0 : p1, nA & 31);       // 0 outside [n_lo, n_hi)
+            const float pB = __shfl_sync(0xffffffffu, (g + 1 < 8) ? p0 : p1, nB & 31);
+            const uint32_t aA = base + (uint32_t)(nA * 128 + ((c ^ (nA & 7)) << 4));
+            const uint32_t aB = base + (uint32_t)(nB * 128 + ((c ^ (nB & 7)) << 4));
+            const uint4 hA = lds128(aA), lA = lds128(aA + AF_KB_BYTES / 2);
+            const uint4 hB = lds128(aB), lB = lds128(aB + AF_KB_BYTES / 2);
+            fma_chunk(acc, accl, hA, lA, pA);
+            fma_chunk(acc, accl, hB, lB, pB);
+          }
+          if (g == g_end) {
+            const int nA = 4 * g + rs;
+            const float pA = __shfl_sync(0xffffffffu, (g < 8) ? p0 : p1, nA & 31);
+            const uint32_t aA = base + (uint32_t)(nA * 128 + ((c ^ (nA & 7)) << 4));
+            const uint4 hA = lds128(aA), lA = lds128(aA + AF_KB_BYTES / 2);
+            fma_chunk(acc, accl, hA, lA, pA);
           }
           if (bend <= nvalid) {
             // ---- the buyer is complete: F.normalize(p=2, dim=1, eps=1e-12) (buyer_tower.py:99) -------
@@ -421,7 +463,8 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
             float ss = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float a = acc[i];
+              const float2 lf = __half22float2(accl[i >> 1]);
+              float a = acc[i] + ((i & 1) ? lf.y : lf.x);
               a += __shfl_xor_sync(0xffffffffu, a, 8);
               a += __shfl_xor_sync(0xffffffffu, a, 16);
               a *= inv;
@@ -436,15 +479,19 @@ attn_pool_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const AttnFus
             named_bar_sync(2, nkb * 32);
             float tot = 0.f;
             for (int j = 0; j < nkb; ++j) tot += sq[j];
-            const float denom = fmaxf(sqrtf(tot), 1e-12f);
+            const float rden = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
             if (rs == 0) {
               float4* op = reinterpret_cast<float4*>(p.out + ((long long)b0 + bl) * p.D + pw * 64 + c * 8);
-              op[0] = make_float4(acc[0] / denom, acc[1] / denom, acc[2] / denom, acc[3] / denom);
-              op[1] = make_float4(acc[4] / denom, acc[5] / denom, acc[6] / denom, acc[7] / denom);
+              op[0] = make_float4(acc[0] * rden, acc[1] * rden, acc[2] * rden, acc[3] * rden);
+              op[1] = make_float4(acc[4] * rden, acc[5] * rden, acc[6] * rden, acc[7] * rden);
             }
             ++nfin;
+            ++bl;
+            next_end += S;
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) accl[i] = __float2half2_rn(0.f);
             m_run = -INFINITY;
             l_run = 0.f;
           }
