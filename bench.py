@@ -64,28 +64,41 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.lines, self.t0, self.t1 = gpu_index, None, [], 0.0, float("inf")
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln))
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
+            # nvidia-smi needs a few hundred ms to start: a short timed region would end before its first sample
+            deadline = time.perf_counter() + 3.0
+            while not self.lines and time.perf_counter() < deadline:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+        self.t0 = time.perf_counter()
         return self
 
     def __exit__(self, *a):
+        self.t1 = time.perf_counter()
         if self.proc:
-            time.sleep(0.25)
+            time.sleep(0.12)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for ts, ln in self.lines if self.t0 <= ts <= self.t1 + 0.06]      # samples of the timed region
+        if not inside:                                                                 # (region shorter than one period)
+            inside = [ln for ts, ln in self.lines if ts >= self.t0][:2]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
