@@ -646,12 +646,20 @@ def run_search(args):
     _native.check(lib.tt_profile_scan_arm(args.steps), "tt_profile_scan_arm")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
+    host_s = [0.0]
+
+    def submit_timed(i):        # host time spent enqueueing (ctypes + Python), to tell a host-bound step from a device-bound one
+        t = time.perf_counter()
+        r = searcher.search_async(queries[i], k)
+        host_s[0] += time.perf_counter() - t
+        return r
     with ClockSampler(local) as clk:
         e0.record()
-        uncertified, last = run_pipelined(lambda i: searcher.search_async(queries[i], k), args.warmup, total, depth)
+        uncertified, last = run_pipelined(submit_timed, args.warmup, total, depth)
         e1.record()
         barrier(world)
     ms_total = max_over_ranks(e0.elapsed_time(e1), world)
+    host_enqueue_ms = max_over_ranks(host_s[0] * 1e3, world) / args.steps
     launches = lib.tt_kernel_launch_count() - launches0
     scan_ms = (torch.empty(args.steps, dtype=torch.float32))
     n_rec = lib.tt_profile_scan_read(scan_ms.data_ptr(), args.steps)
@@ -702,6 +710,7 @@ def run_search(args):
                                     if world > 1 else "none"),
                        "l2": f"inputs ({n_local * dp * 2 / 1e9:.2f} GB bf16 per pass per GPU) exceed L2; no flush"},
             "e2e": e2e, "gpu_launches": int(launches), "uncertified_queries": uncertified,
+            "host_enqueue_ms_per_step": host_enqueue_ms,
             "roofline": roofline, "parity": parity, "clocks": clocks}
     if world == 1 and not args.no_secondary:
         sec = {"pooling": bench_pooling(peaks),

@@ -24,12 +24,11 @@ with torch.no_grad():
 torch.cuda.synchronize()
 rows = [[int(v) for v in l.split()] for l in open(path)]
 base = min(v for r in rows for v in r if v > 0)
-names = {1: "buf_free seen", 0: "tma issued", 2: "raw0", 3: "raw1", 4: "raw2", 5: "raw3", 6: "raw4", 7: "raw5",
-         8: "split0", 9: "split1", 10: "split2", 11: "split3", 12: "split4", 13: "split5",
-         14: "mma_sees0", 15: "mma_sees1", 16: "mma_sees2", 17: "mma_sees3", 18: "mma_sees4", 19: "mma_sees5",
-         25: "acc_empty seen", 20: "commit issued", 21: "epi sees acc_full", 22: "logits written", 23: "pool sees logits", 24: "pool done"}
-order = [1, 0, 2, 8, 14, 3, 9, 15, 4, 10, 16, 5, 11, 17, 6, 12, 18, 7, 13, 19, 25, 20, 21, 22, 23, 24]
 for t, r in enumerate(rows):
     if r[0] == 0:
         continue
-    print(f"tile {t:2d} @ {r[1] - base:7d}: " + " ".join(f"{names[i]}={r[i] - r[1]}" for i in order[1:]))
+    t0 = r[0]
+    f = lambda i: r[i] - t0 if r[i] else None
+    print(f"tile {t:2d} @ {t0 - base:7d}: " + " | ".join(
+        f"kb{kb}: tma {f(kb)} raw {f(6 + kb)} split {f(12 + kb)} mma_sees {f(18 + kb)} commit {f(24 + kb)}" for kb in range(6))
+        + f" | epi sees {f(30)} epi done {f(31)}")
