@@ -56,7 +56,6 @@ int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long l
 
 // shared TMA descriptor helper (flat_scan.cu) and the tensor-core attention-logits launcher (attn_logits_tc.cu)
 int make_tmap_f32(void* tensor_map /* CUtensorMap* */, const void* base, long long rows, int cols, int box_rows, int box_cols);
-int make_tmap_16bit(void* tensor_map /* CUtensorMap* */, const void* base, long long rows, int pitch, int box_rows);
 int launch_attn_logits_tc(const float* x, long long R, int D, const float* W1, const float* b1, const float* W2,
                           const float* b2, int H, float* logits, cudaStream_t st);
 

@@ -620,11 +620,6 @@ static int encode_tmap_bf16(CUtensorMap* m, const void* base, long long rows, in
   return TT_OK;
 }
 
-// 16-bit elements [rows, pitch] row-major, box = [box_rows, 64 columns], 128-byte swizzle (uncached: one-off maps)
-int make_tmap_16bit(void* tensor_map, const void* base, long long rows, int pitch, int box_rows) {
-  return encode_tmap_bf16(reinterpret_cast<CUtensorMap*>(tensor_map), base, rows, pitch, box_rows);
-}
-
 // fp32 [rows, cols] row-major (row pitch = cols*4 bytes, a multiple of 16), box = [box_rows, box_cols <= 32],
 // 128-byte swizzle, out-of-range rows/columns read as 0.
 int make_tmap_f32(void* tensor_map, const void* base, long long rows, int cols, int box_rows, int box_cols) {
