@@ -45,7 +45,7 @@ def main():
     traffic_path = ROOT / "profiles" / "scan_traffic.json"
     traffic = json.loads(traffic_path.read_text()) if traffic_path.exists() else {}
     print(f"# ncu --set full summaries ({tag})\n")
-    print("Captured with `ncu --set full --clock-control none --import-source on` on one B200 (see tools/gpu_r01_evidence.sh);")
+    print("Captured with `ncu --set full --clock-control none --import-source on` on one B200 (see tools/gpu_r0N_evidence.sh);")
     print("per-launch values, cold cache, serialised; durations are NOT bench values.\n")
     print("| report | kernel | grid | " + " | ".join(n for _, n in METRICS) + " |")
     print("|---|---|---|" + "---|" * len(METRICS))
@@ -69,11 +69,11 @@ def main():
                     cells.append("-")
             k = short(r[ix["Kernel Name"]])
             print(f"| {Path(rep).stem} | `{k}` | {r[ix['Grid Size']]} | " + " | ".join(cells) + " |")
-            m = re.match(r"scan_nq(\d+)", Path(rep).stem)
+            m = re.search(r"scan_nq(\d+)", Path(rep).stem)
             if m and re.search(r"flat_scan_kernel<\(int\)\d+, \(bool\)0|flat_scan_kernel<\d+, 0", r[ix["Kernel Name"]]):
                 rd = float(r[ix["dram__bytes_read.sum"]]) * UNIT.get(units[ix["dram__bytes_read.sum"]], 1.0)
                 wr = float(r[ix["dram__bytes_write.sum"]]) * UNIT.get(units[ix["dram__bytes_write.sum"]], 1.0)
-                traffic[f"nq{m.group(1)}"] = rd + wr
+                traffic[f"10000000x384_nq{m.group(1)}"] = rd + wr        # the evidence scripts capture the headline catalog
     traffic_path.write_text(json.dumps(traffic, indent=1, sort_keys=True) + "\n")
 
 

@@ -43,10 +43,10 @@ int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N,
 // the pieces launch_scan is made of (the sharded path runs them with an exchange in between)
 ScanPlan make_shard_plan(long long N_local, long long N_total, int D, int nq, int K, bool* global_ok);
 int launch_sample(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr, float* topr,
-                  float* sample_buf, cudaStream_t st);
+                  float* sample_buf, cudaStream_t st, bool skip_select = false);
 int launch_select_gathered(const float* topr_g, int G, int nq, int r, float* thr, int* zero_me, cudaStream_t st);
 int launch_main_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr,
-                     unsigned int* seg_cnt, void* cand, cudaStream_t st);
+                     unsigned int* seg_cnt, void* cand, cudaStream_t st, const float* sel_sample = nullptr);
 
 // fp32 rescoring of every candidate, exact sort, certificate
 int launch_finalize(const ScanPlan& pl, const float* qn, const float* Xn, long long N, int D, int nq, int K,

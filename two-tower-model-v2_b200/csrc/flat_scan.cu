@@ -196,7 +196,22 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const bool valid = (q_local >= 0) && (q < p.nq);
 
     float thr = INFINITY;
-    if (!SAMPLE && valid) thr = __ldg(p.thr + q);
+    if (!SAMPLE) {
+      if (p.sel_n > 0) {
+        // small batches: no separate selection kernel - the 128 epilogue threads pick the thresholds from the sampled
+        // maxima (one query after the other) while the producer and the MMA warp already stream the first tile
+        uint32_t* sel_tmp = reinterpret_cast<uint32_t*>(bars) + 48;      // two free words of the barrier block
+        for (int qq = 0; qq < p.nq; ++qq) {
+          const float t = epilogue_select(p.sel_sample, p.sel_n, p.sel_ld, qq, p.sel_query_major, p.sel_rank, scratch_base,
+                                          sel_tmp, (int)threadIdx.x - 128);
+          if (q == qq) thr = t;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // the histogram doubles as the warps' scratch rows
+        if (blockIdx.x == 0 && valid) p.thr_out[q] = thr;
+      } else if (valid) {
+        thr = __ldg(p.thr + q);
+      }
+    }
     uint2* my_cand = SAMPLE ? nullptr : (p.cand + ((size_t)(valid ? q : 0) * p.nslices + slice) * p.seg_cap);
     unsigned int my_cnt = 0;
     uint32_t* scratch = scratch_base + (warp - 4) * 64;
@@ -835,13 +850,21 @@ static int make_scan_params(const ScanPlan& pl, const void* qh, const void* Xh, 
 
 // Sample pass + selection.  thr != NULL: the query's threshold; topr != NULL (tile mode only): its
 // SHARD_TOPR largest sampled tile maxima, descending (sharded catalogs exchange these lists).
+// Batches of <= 4 queries on the single tiling: the main scan selects the thresholds itself (epilogue_select).
+static bool fold_select(const ScanPlan& pl, int nq) {
+  static const bool on = [] { const char* e = getenv("TT_B200_FOLD_SELECT"); return !(e && e[0] == '0'); }();
+  const int nvals = pl.sample_tile_max ? pl.sample_slots : pl.sample_slots * CHUNKS;
+  return on && nq <= 4 && !pl.pair && pl.nqu == 1 && nvals <= 4096;
+}
+
 int launch_sample(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr, float* topr,
-                  float* sample_buf, cudaStream_t st) {
+                  float* sample_buf, cudaStream_t st, bool skip_select) {
   CUtensorMap tq, tx;
   ScanParams sp;
   if (int e = make_scan_params(pl, qh, Xh, N, nq, thr, nullptr, nullptr, sample_buf, &tq, &tx, &sp)) return e;
   sp.num_slots = pl.sample_slots; sp.tile_stride = pl.sample_stride; sp.nslices = pl.sample_slices;
   if (int e = launch_scan_mode<true>(pl, tq, tx, sp, pl.sample_slices * pl.nqu, st)) return e;
+  if (skip_select) return TT_OK;
   {
     // few values per query: CTA-wide radix select (query-minor tile maxima only for small batches: a CTA reads one
     // 4-byte value per sampled tile row there)
@@ -892,11 +915,16 @@ int launch_select_gathered(const float* topr_g, int G, int nq, int r, float* thr
 }
 
 int launch_main_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr,
-                     unsigned int* seg_cnt, void* cand, cudaStream_t st) {
+                     unsigned int* seg_cnt, void* cand, cudaStream_t st, const float* sel_sample) {
   CUtensorMap tq, tx;
   ScanParams sp;
   if (int e = make_scan_params(pl, qh, Xh, N, nq, thr, seg_cnt, cand, nullptr, &tq, &tx, &sp)) return e;
   sp.num_slots = pl.num_tiles; sp.tile_stride = 1; sp.nslices = pl.main_slices;
+  if (sel_sample) {       // thresholds selected in the kernel's prologue from the sample pass's maxima
+    sp.sel_sample = sel_sample; sp.thr_out = thr;
+    sp.sel_n = pl.sample_tile_max ? pl.sample_slots : pl.sample_slots * CHUNKS;
+    sp.sel_ld = pl.nq_pad; sp.sel_rank = pl.sample_rank; sp.sel_query_major = pl.sample_tile_max ? 0 : 1;
+  }
   profile_scan_begin(st);
   const int e = launch_scan_mode<false>(pl, tq, tx, sp, pl.main_slices * pl.nqu, st);
   profile_scan_end(st);
@@ -905,13 +933,15 @@ int launch_main_scan(const ScanPlan& pl, const void* qh, const void* Xh, long lo
 
 int launch_scan(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq,
                 float* thr, unsigned int* seg_cnt, void* cand, float* sample_buf, cudaStream_t st) {
+  bool fold = false;
   if (pl.use_threshold) {
-    if (int e = launch_sample(pl, qh, Xh, N, nq, thr, nullptr, sample_buf, st)) return e;
+    fold = fold_select(pl, nq);
+    if (int e = launch_sample(pl, qh, Xh, N, nq, thr, nullptr, sample_buf, st, fold)) return e;
   } else {
     count_launch();
     TT_CHECK_CUDA(launch_pdl(fill_kernel, dim3((nq + 255) / 256), dim3(256), 0, st, thr, nq, -INFINITY));
   }
-  return launch_main_scan(pl, qh, Xh, N, nq, thr, seg_cnt, cand, st);
+  return launch_main_scan(pl, qh, Xh, N, nq, thr, seg_cnt, cand, st, fold ? sample_buf : nullptr);
 }
 
 // Plan of one shard of a catalog of N_total rows: tiling and slicing follow the shard, the sampling

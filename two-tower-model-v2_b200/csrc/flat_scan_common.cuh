@@ -38,6 +38,11 @@ struct ScanParams {
   unsigned int* seg_cnt;  // [nq, nslices]
   uint2* cand;            // [nq, nslices, seg_cap]  (score bits, row)
   int seg_cap;
+  // MAIN with the threshold selection folded into the prologue (batches of <= 4 queries): thr[q] = the sel_rank-th
+  // largest of the query's sel_n sampled maxima, computed by the epilogue warps while the first tile streams in
+  const float* sel_sample;
+  float* thr_out;         // [nq] written by CTA 0 for the finalize kernel
+  int sel_n, sel_ld, sel_rank, sel_query_major;
   // SAMPLE
   float* sample_out;      // chunk mode: [nq_pad, num_slots, 8] maxima of the 32-row chunks of every sampled tile
                           // tile mode : [num_slots, sample_ld] maximum of every sampled tile (query fastest)
@@ -81,6 +86,59 @@ static __device__ __noinline__ void append_columns(uint32_t taddr, int ncols, fl
       }
     }
   }
+}
+// r-th largest of the n <= 4096 sampled maxima of query q, by the 128 epilogue threads of a CTA (et = 0..127): the
+// values sit in registers as order-preserving keys, four 8-bit radix passes over a 256-bin shared-memory histogram
+// (`hist`, 1 KB) fix the key byte by byte; `tmp` = two words of shared memory.  Named barrier 1 (128 threads).
+static __device__ __noinline__ float epilogue_select(const float* __restrict__ sample, int n, int ld, int q, int query_major,
+                                                     int r, uint32_t* hist, uint32_t* tmp, int et) {
+  constexpr int VPT = 32;
+  uint32_t key[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int idx = et + i * 128;
+    // padding key 0 sorts below every value, -inf included: it can never be among the r <= n largest
+    key[i] = (idx < n) ? float_to_ordered(query_major ? __ldg(sample + (size_t)q * n + idx) : __ldg(sample + (size_t)idx * ld + q)) : 0u;
+  }
+  if (n < r) return -INFINITY;
+  uint32_t prefix = 0u, mask = 0u;
+  unsigned int kk = (unsigned int)r;
+  const int lane = et & 31;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[et] = 0u;
+    hist[et + 128] = 0u;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      if ((key[i] & mask) == prefix) atomicAdd(&hist[(key[i] >> shift) & 255u], 1u);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (et < 32) {
+      // lane l owns bins 255-8l .. 248-8l (descending)
+      unsigned int loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { loc[j] = hist[255 - 8 * lane - j]; sum += loc[j]; }
+      unsigned int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      const unsigned int excl = incl - sum;
+      if (excl < kk && incl >= kk) {           // exactly one lane
+        unsigned int above = excl;
+        int d = 255 - 8 * lane - 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (above + loc[j] >= kk) { d = 255 - 8 * lane - j; break; }
+          above += loc[j];
+        }
+        tmp[0] = (uint32_t)d;
+        tmp[1] = kk - above;
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    prefix |= tmp[0] << shift;
+    mask |= 255u << shift;
+    kk = tmp[1];
+  }
+  return ordered_to_float(prefix);
 }
 static __device__ __noinline__ float max_columns(uint32_t taddr, int ncols) {
   float m = -INFINITY;
