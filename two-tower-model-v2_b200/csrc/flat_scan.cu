@@ -198,8 +198,8 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     float thr = INFINITY;
     if (!SAMPLE) {
       if (p.sel_n > 0) {
-        // small batches: no separate selection kernel - the 128 epilogue threads pick the thresholds from the sampled
-        // maxima (one query after the other) while the producer and the MMA warp already stream the first tile
+        // batch of one: no separate selection kernel - the 128 epilogue threads pick the threshold from the sampled
+        // maxima while the producer and the MMA warp already stream the first tile
         uint32_t* sel_tmp = reinterpret_cast<uint32_t*>(bars) + 48;      // two free words of the barrier block
         for (int qq = 0; qq < p.nq; ++qq) {
           const float t = epilogue_select(p.sel_sample, p.sel_n, p.sel_ld, qq, p.sel_query_major, p.sel_rank, scratch_base,
@@ -850,11 +850,13 @@ static int make_scan_params(const ScanPlan& pl, const void* qh, const void* Xh, 
 
 // Sample pass + selection.  thr != NULL: the query's threshold; topr != NULL (tile mode only): its
 // SHARD_TOPR largest sampled tile maxima, descending (sharded catalogs exchange these lists).
-// Batches of <= 4 queries on the single tiling: the main scan selects the thresholds itself (epilogue_select).
+// A single query (the batch-1 serving call): the main scan selects the threshold itself (epilogue_select).  Measured at
+// 1M x 384: 150.4 vs 155.2 us per step at nq = 1; at nq = 4 the four selections in a row delay the first epilogue
+// enough to stall the MMAs (174.9 vs 158.3 us), so larger batches keep the separate kernel.
 static bool fold_select(const ScanPlan& pl, int nq) {
   static const bool on = [] { const char* e = getenv("TT_B200_FOLD_SELECT"); return !(e && e[0] == '0'); }();
   const int nvals = pl.sample_tile_max ? pl.sample_slots : pl.sample_slots * CHUNKS;
-  return on && nq <= 4 && !pl.pair && pl.nqu == 1 && nvals <= 4096;
+  return on && nq == 1 && !pl.pair && pl.nqu == 1 && nvals <= 4096;
 }
 
 int launch_sample(const ScanPlan& pl, const void* qh, const void* Xh, long long N, int nq, float* thr, float* topr,

@@ -38,7 +38,7 @@ struct ScanParams {
   unsigned int* seg_cnt;  // [nq, nslices]
   uint2* cand;            // [nq, nslices, seg_cap]  (score bits, row)
   int seg_cap;
-  // MAIN with the threshold selection folded into the prologue (batches of <= 4 queries): thr[q] = the sel_rank-th
+  // MAIN with the threshold selection folded into the prologue (a batch of one query): thr[q] = the sel_rank-th
   // largest of the query's sel_n sampled maxima, computed by the epilogue warps while the first tile streams in
   const float* sel_sample;
   float* thr_out;         // [nq] written by CTA 0 for the finalize kernel

@@ -196,7 +196,11 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
   // ---- 4. fp32 rescoring of the m survivors (in place) --------------------------------------------
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(Xn) & 15) == 0);
   int bad = 0;   // self-check: a candidate's tensor-core score must match its fp32 rescoring within eps
-  constexpr int U = 4;   // candidates rescored concurrently per warp (independent loads in flight)
+  // candidates rescored concurrently per warp.  The wide CTA of a small batch is latency-bound: 2 rows with every
+  // 16-byte piece in flight at once (18.6 vs 21.4 us at nq = 1); the 256-thread CTAs of large batches are
+  // throughput-bound and keep 4 rows x one piece (the wide scheme there: 45 vs 35 us at nq = 128, 294 vs 261 us at 4096)
+  constexpr bool WIDE = FIN_THREADS > 512;
+  constexpr int U = WIDE ? 2 : 4;
   for (int i0 = warp * U; i0 < m; i0 += NWARPS * U) {
     uint32_t row[U];
     float bsc[U];
@@ -211,7 +215,33 @@ flat_finalize_kernel(const float* __restrict__ qn, const float* __restrict__ Xn,
       ok[u] = (i < m) && ((long long)row[u] < N);   // row >= N cannot happen unless the scan is broken
       a[u] = 0.f;
     }
-    if (vec) {
+    if (WIDE && vec && D <= 512) {
+      // every 16-byte piece of the U rows is requested before the first one is used: one memory latency per round
+      // instead of one per 128 columns (the rows are scattered over the table: DRAM or, after the prefetch, L2)
+      constexpr int NVX = 4;
+      const float4* q4 = reinterpret_cast<const float4*>(qs);
+      const int nvec = D >> 2;
+      float4 x[U][NVX];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float4* rp = reinterpret_cast<const float4*>(Xn + (long long)row[u] * D);
+#pragma unroll
+        for (int v = 0; v < NVX; ++v) {
+          const int cc = v * 32 + lane;
+          x[u][v] = (ok[u] && cc < nvec) ? __ldg(rp + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < NVX; ++v) {
+        const int cc = v * 32 + lane;
+        const float4 y = (cc < nvec) ? q4[cc] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          a[u] = fmaf(x[u][v].x, y.x, a[u]); a[u] = fmaf(x[u][v].y, y.y, a[u]);
+          a[u] = fmaf(x[u][v].z, y.z, a[u]); a[u] = fmaf(x[u][v].w, y.w, a[u]);
+        }
+      }
+    } else if (vec) {
       const float4* q4 = reinterpret_cast<const float4*>(qs);
       for (int cc = lane; cc < (D >> 2); cc += 32) {
         const float4 y = q4[cc];
