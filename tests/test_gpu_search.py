@@ -66,6 +66,7 @@ def test_scan_scores_match_bf16_reference(N, D, nq):
     (20000, 384, 64, 10),      # C1 catalog / k
     (20000, 384, 2000, 10),    # C1 full query count (16 query blocks)
     (100000, 384, 1, 100), (100000, 384, 7, 100), (100000, 384, 129, 100), (50000, 384, 300, 1),
+    (300000, 128, 1, 10), (100000, 384, 2, 100),   # nq = 1: threshold selected inside the main scan; nq = 2: radix-select kernel
     (30000, 768, 50, 100),     # C4 width (M=64 path)
     (60000, 768, 300, 100),    # C4 width, CTA pairs with a half-resident query block
     (30000, 100, 33, 37),      # D not a multiple of 64
