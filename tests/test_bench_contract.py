@@ -83,3 +83,24 @@ def test_parity_comparator_tie_rules():
     other = torch.tensor([[10, 11, 12, 99]])
     assert bench.compare_topk_device(rs, other, rs, ri)["ok"]                               # boundary tie (same score)
     assert not bench.compare_topk_device(rs - torch.tensor([[0, 0, 0, 5e-6]]), other, rs, ri)["ok"]
+
+
+def test_clock_sampler_keeps_only_samples_of_the_timed_region():
+    """bench.ClockSampler.summary: samples stamped outside [enter, exit] are dropped (nvidia-smi starts before the timed
+    region and runs past it); a region shorter than one sampling period falls back to the first samples after its start."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    row = "{sm}, 1965, 700.0, Not Active, Not Active, Not Active, {cap}\n"
+    cs = bench.ClockSampler(0)
+    cs.t0, cs.t1 = 10.0, 11.0
+    cs.lines = [(9.5, row.format(sm=300, cap="Not Active")), (10.2, row.format(sm=1650, cap="Active")),
+                (10.6, row.format(sm=1700, cap="Active")), (11.5, row.format(sm=200, cap="Not Active"))]
+    out = cs.summary()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1675.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"]
+    cs.t0, cs.t1 = 10.0, 10.01                       # 10 ms region: no sample inside
+    cs.lines = [(9.9, row.format(sm=300, cap="Not Active")), (10.05, row.format(sm=1900, cap="Not Active"))]
+    out = cs.summary()
+    assert out["samples"] == 1 and out["sm_mhz"] == 1900.0 and out["reasons"] == []
+    cs.lines = []
+    assert cs.summary()["sm_mhz"] is None
