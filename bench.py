@@ -654,6 +654,7 @@ def run_search(args):
         host_s[0] += time.perf_counter() - t
         return r
     with ClockSampler(local) as clk:
+        barrier(world)          # the sampler's start-up time differs between ranks: line them up again before the clock starts
         e0.record()
         uncertified, last = run_pipelined(submit_timed, args.warmup, total, depth)
         e1.record()
@@ -806,6 +807,7 @@ def run_c5(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
     with ClockSampler(local) as clk:
+        barrier(world)          # (the sampler's start-up time differs between ranks)
         e0.record()
         uncertified, last = run_pipelined(lambda i: pipe.retrieve_device_async(*big_dev[i], k), args.warmup, total)
         e1.record()
