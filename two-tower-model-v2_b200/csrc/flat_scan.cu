@@ -31,9 +31,11 @@
 //
 // Two epilogue modes:
 //   SAMPLE : scan every `tile_stride`-th tile and write only the maximum score of each 32-row
-//            chunk per query; select_threshold_kernel takes the r-th largest of those maxima as
-//            the query's threshold.  Chunk maxima are scores of distinct rows, so the threshold
-//            is a guaranteed lower bound of the r-th best bf16 score of the whole catalog.
+//            chunk (or of the whole tile) per query; the r-th largest of those maxima becomes the
+//            query's threshold (select_threshold_radix_kernel / select_threshold_tile_kernel, or -
+//            for a batch of one - the main scan's own prologue, epilogue_select).  The maxima are
+//            scores of distinct rows, so the threshold is a guaranteed lower bound of the r-th best
+//            bf16 score of the whole catalog.
 //   MAIN   : scan every tile, append scores >= threshold.
 #include <cuda.h>
 #include <math.h>
