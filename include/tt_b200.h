@@ -12,6 +12,7 @@
  * arithmetic it replaces:
  *
  *   src/models/buyer_tower.py:43-68    weighted_average        -> tt_pool_weighted[_gather]
+ *   src/training/losses.py:36-79       InfoNCELoss.forward     -> tt_infonce_forward / tt_infonce_backward
  *   src/models/buyer_tower.py:70-101   attention_aggregation   -> tt_pool_attention_fused (dense), tt_attention_logits + tt_pool_attention[_gather]
  *   src/inference/vector_db.py:44-54   build_index (normalise + IndexFlatIP.add) -> tt_flat_build
  *   src/inference/vector_db.py:152-160 retrieve  (renormalise + IndexFlatIP.search) -> tt_flat_search
@@ -100,6 +101,20 @@ int tt_pool_attention_gather(const float* table, int64_t N, const float* row_log
  * with dy = (g - out (out.g)) / ||y|| (F.normalize), coefficients as in the forward.  D % 4 == 0, D <= 1024. */
 int tt_pool_backward(const float* x, const float* w, const float* logits, const float* g,
                      float* dx, float* dw, float* dlogit, int B, int S, int D, void* stream);
+
+/* InfoNCE loss of the training callers (src/training/losses.py:36-79; trainer.py:216-236): for buyer embeddings
+ * b f32 [B,D], positive product embeddings p f32 [B,D] and sampled negatives n f32 [B,M,D] (M may be 0, then n may be
+ * NULL) the logits of row i are [ b_i.p_i | b_i.n_ij (j < M) | b_i.p_k (k != i, the masked in-batch block) ] / T and
+ *   loss[0] = mean_i row_loss[i],  row_loss[i] = lse[i] - b_i.p_i / T,  lse[i] = logsumexp(logits_i)
+ * (F.cross_entropy with label 0).  Neither the [B,B,D] expansion nor the logits matrix is materialised.  D <= 1024.
+ * tt_infonce_backward: grad_loss = device pointer to dL/dloss (one float); writes d_buyer [B,D], d_pos [B,D] and
+ * d_neg [B,M,D] (NULL when M == 0).  workspace: tt_infonce_workspace_bytes(B) bytes of device memory. */
+size_t tt_infonce_workspace_bytes(int B);
+int tt_infonce_forward(const float* buyer, const float* pos, const float* neg, int B, int M, int D, float temperature,
+                       float* loss, float* row_loss, float* lse, void* stream);
+int tt_infonce_backward(const float* buyer, const float* pos, const float* neg, const float* lse, const float* grad_loss,
+                        int B, int M, int D, float temperature, float* d_buyer, float* d_pos, float* d_neg,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Pooling out of a row-SHARDED item table (BASELINE config C5: the catalog, which is the item table of the
  * /retrieve path - src/inference/encoder.py:276-303 pools the item embeddings of the history - is split over the

@@ -342,3 +342,21 @@ def test_micro_batcher_hands_out_array_rows_without_python_lists():
         ids, scores = out[c]
         assert len(out[c]) == 3 + c % 4 and ids[0] == 100 * c and np.allclose(scores, ids / 7)
     assert sum(calls) == 20 and max(calls) <= 8
+
+
+def test_infonce_loss_surface_and_no_cpu_fallback():
+    """Same constructor / forward signature as the reference InfoNCELoss (losses.py:8-36); CPU tensors raise (there is no
+    CPU path), malformed shapes raise ValueError before anything is launched."""
+    import torch
+    from two_tower_model_v2_b200 import InfoNCELoss
+    crit = InfoNCELoss()
+    assert crit.temperature == 0.07 and InfoNCELoss(temperature=0.2).temperature == 0.2
+    b, p, n = torch.randn(4, 8), torch.randn(4, 8), torch.randn(4, 2, 8)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        crit(b, p, n)
+    with pytest.raises(ValueError):
+        crit(b, torch.randn(5, 8), n)
+    with pytest.raises(ValueError):
+        crit(b, p, torch.randn(4, 8))
+    with pytest.raises(ValueError):
+        crit(b, p, torch.randn(3, 2, 8))

@@ -115,3 +115,31 @@ def test_eager_backward_formulation_matches_reference_outputs(name):
     mlp = tuple(torch.from_numpy(g[k]) for k in ("W1", "b1", "W2", "b2"))
     at = _eager_pool(x, w, mlp).numpy()
     assert rel_err(at, g["attention"]) < 1e-5
+
+
+INFONCE_CASES = sorted(p.name for p in GOLDEN.glob("infonce_*.npz"))
+
+
+@pytest.mark.parametrize("case", INFONCE_CASES)
+def test_infonce_oracle_matches_reference(case):
+    """oracle/infonce_oracle.py (losses.py:36-79) against the loss and the autograd gradients of the real InfoNCELoss."""
+    import torch
+    from oracle import infonce_oracle as io
+    g = golden(case)
+    b, p, n, t = g["buyer"], g["pos"], g["neg"], float(g["temperature"])
+    loss, row, lse = io.loss(b, p, n, t)
+    assert abs(loss - g["loss"]) <= 1e-5 * max(1.0, abs(g["loss"]))
+    l64, _, _ = io.loss(b.astype(np.float64), p.astype(np.float64), n.astype(np.float64), t)
+    assert abs(l64 - g["loss_f64"]) <= 1e-10 * max(1.0, abs(g["loss_f64"]))
+    assert row.shape == (b.shape[0],) and np.allclose(row.mean(), loss)
+    db, dp, dn = io.gradients(b.astype(np.float64), p.astype(np.float64), n.astype(np.float64), t)
+    for mine, ref in ((db, g["d_buyer"]), (dp, g["d_pos"]), (dn, g["d_neg"])):
+        assert mine.shape == ref.shape
+        if ref.size:
+            assert np.abs(mine - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-30)
+    tl = io.torch_loss(torch.from_numpy(b), torch.from_numpy(p), torch.from_numpy(n), t)
+    assert abs(tl.item() - g["loss"]) <= 1e-5 * max(1.0, abs(g["loss"]))
+
+
+def test_infonce_golden_present():
+    assert len(INFONCE_CASES) >= 5

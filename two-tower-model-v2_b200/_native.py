@@ -28,6 +28,10 @@ SIGNATURES = {
     "tt_pool_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tt_pool_attention_gather": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tt_pool_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tt_infonce_workspace_bytes": (c_size_t, [c_int]),
+    "tt_infonce_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tt_infonce_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tt_pool_partial_gather": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_float, c_void_p, c_void_p,
                                        c_void_p, c_int, c_int, c_int, c_void_p]),
     "tt_pool_partial_merge": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),

@@ -118,6 +118,36 @@ def pool_backward(x: torch.Tensor, w: torch.Tensor, logits, g: torch.Tensor, nee
     return dx, dw, dlogit
 
 
+def infonce_forward(buyer: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, temperature: float):
+    """InfoNCE forward (tt_infonce_forward): buyer/pos f32 [B,D], neg f32 [B,M,D] -> (loss [1], row_loss [B], lse [B])."""
+    B, D = buyer.shape
+    M = neg.shape[1]
+    loss = torch.empty(1, device=buyer.device, dtype=torch.float32)
+    row_loss = torch.empty(B, device=buyer.device, dtype=torch.float32)
+    lse = torch.empty(B, device=buyer.device, dtype=torch.float32)
+    with torch.cuda.device(buyer.device):
+        _native.check(_native.load().tt_infonce_forward(buyer.data_ptr(), pos.data_ptr(), neg.data_ptr() if M else 0, B, M, D,
+                                                        float(temperature), loss.data_ptr(), row_loss.data_ptr(), lse.data_ptr(),
+                                                        _stream()), "tt_infonce_forward")
+    return loss, row_loss, lse
+
+
+def infonce_backward(buyer: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, lse: torch.Tensor, grad_loss: torch.Tensor,
+                     temperature: float):
+    """InfoNCE backward (tt_infonce_backward): grad_loss f32 [1] on the device -> (d_buyer [B,D], d_pos [B,D], d_neg [B,M,D])."""
+    B, D = buyer.shape
+    M = neg.shape[1]
+    lib = _native.load()
+    d_buyer, d_pos, d_neg = torch.empty_like(buyer), torch.empty_like(pos), torch.empty_like(neg)
+    ws = torch.empty(max(int(lib.tt_infonce_workspace_bytes(B)), 256), device=buyer.device, dtype=torch.uint8)
+    with torch.cuda.device(buyer.device):
+        _native.check(lib.tt_infonce_backward(buyer.data_ptr(), pos.data_ptr(), neg.data_ptr() if M else 0, lse.data_ptr(),
+                                              grad_loss.data_ptr(), B, M, D, float(temperature), d_buyer.data_ptr(),
+                                              d_pos.data_ptr(), d_neg.data_ptr() if M else 0, ws.data_ptr(), ws.numel(),
+                                              _stream()), "tt_infonce_backward")
+    return d_buyer, d_pos, d_neg
+
+
 def pool_partial_gather(table: torch.Tensor, row_lo: int, n_total: int, owns_invalid: bool, row_logits, zero_row_logit: float,
                         idx: torch.Tensor, w: torch.Tensor, partial: torch.Tensor = None) -> torch.Tensor:
     """Owner-computes partial pooling over this rank's rows of a sharded item table -> partial f32 [B, D+4]
@@ -225,4 +255,4 @@ def shard_merge(gathered: torch.Tensor, off_scores: int, off_ids: int, off_bound
 
 
 __all__ = ["shard_merge", "flat_build", "flat_search", "flat_search_exact", "pool_weighted", "pool_weighted_gather", "attention_logits", "pool_attention",
-           "pool_attention_gather", "pool_attention_fused", "pool_backward", "pool_partial_gather", "pool_partial_merge", "topk_merge", "_f32c", "_stream"]
+           "pool_attention_gather", "pool_attention_fused", "pool_backward", "infonce_forward", "infonce_backward", "pool_partial_gather", "pool_partial_merge", "topk_merge", "_f32c", "_stream"]
